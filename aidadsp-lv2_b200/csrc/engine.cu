@@ -1,0 +1,712 @@
+// engine.cu -- host side of the C ABI in include/aidax.h: stream/model bookkeeping, control
+// decode, dirty-range uploads, block tables and kernel launches.  CUDA runtime only (no torch).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/aidax.h"
+#include "dsp_host.h"
+#include "layout.h"
+#include "model_host.h"
+#include "variants.h"
+
+namespace aidax {
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t err__ = (expr);                                                             \
+        if (err__ != cudaSuccess)                                                               \
+            return fail(AIDAX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+struct DevArray {
+    T* d = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count)
+    {
+        n = count;
+        cudaError_t e = cudaMalloc((void**)&d, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) e = cudaMemset(d, 0, std::max<size_t>(count, 1) * sizeof(T));
+        return e;
+    }
+    void release() { if (d) cudaFree(d); d = nullptr; n = 0; }
+};
+
+struct ModelEntry {
+    HostModel host;
+    float* d_weights = nullptr;
+};
+
+struct Family {       // one kernel family = (cell, hidden); cell 2 = streams without a network
+    int cell, H;
+    std::vector<const KernelVariant*> variants; // sorted by S ascending
+};
+
+struct LaunchPlan {
+    const KernelVariant* kv = nullptr;
+    int n_blocks = 0;
+    size_t tbl_offset_model = 0; // offsets into the uploaded table buffers (ints)
+    size_t tbl_offset_slots = 0;
+    int max_param_tiles = 0;
+};
+
+} // namespace aidax
+
+using namespace aidax;
+
+struct aidax_engine {
+    int device = 0;
+    int cap = 0;
+    int max_block = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    int tile_mode = 0, math_mode = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    uint64_t launches = 0;
+
+    // host shadows
+    std::vector<StreamHost> streams;
+    int n_open_hi = 0; // one past the highest stream id ever opened
+    std::vector<uint8_t> dirty_ctrl, dirty_coef, dirty_cmd;
+    std::vector<uint32_t> h_flags, h_cmd;
+    std::vector<float> h_pre_target, h_master_target, h_p_port, h_p_init, h_cmd_pre_mem, h_cmd_master_mem, h_exp_coef, h_lin_denom;
+    std::vector<double> h_bq_coef;
+    bool any_dirty = false;
+
+    // device arrays
+    DevArray<uint32_t> d_flags, d_cmd, d_dflags;
+    DevArray<float> d_pre_target, d_master_target, d_p_port, d_p_init, d_cmd_pre_mem, d_cmd_master_mem, d_exp_coef, d_lin_denom;
+    DevArray<float> d_pre_mem, d_master_mem, d_p_mem, d_p_step, d_p_target, d_rnn;
+    DevArray<double> d_bq_coef, d_bq_z;
+    DevArray<float> d_io_in, d_io_out;
+    DevArray<ModelDev> d_models;
+    DevArray<int> d_tables;
+    std::vector<int> h_tables;
+
+    std::vector<ModelEntry> models;
+    std::map<std::string, int> model_cache;
+    bool models_dirty = false;
+
+    std::vector<Family> families;
+    // plan cache
+    uint64_t membership_epoch = 1, plan_epoch = 0;
+    int plan_first = -1, plan_n = -1, plan_tile_mode = -1;
+    std::vector<LaunchPlan> plan;
+    std::vector<const void*> attr_done;
+
+    StreamArrays sa() const
+    {
+        StreamArrays a{};
+        a.flags = d_flags.d; a.cmd = d_cmd.d; a.pre_target = d_pre_target.d; a.master_target = d_master_target.d;
+        a.p_port = d_p_port.d; a.p_init = d_p_init.d; a.cmd_pre_mem = d_cmd_pre_mem.d; a.cmd_master_mem = d_cmd_master_mem.d;
+        a.exp_coef = d_exp_coef.d; a.lin_denom = d_lin_denom.d; a.bq_coef = d_bq_coef.d;
+        a.dflags = d_dflags.d; a.pre_mem = d_pre_mem.d; a.master_mem = d_master_mem.d; a.p_mem = d_p_mem.d;
+        a.p_step = d_p_step.d; a.p_target = d_p_target.d; a.bq_z = d_bq_z.d; a.rnn = d_rnn.d; a.cap = cap;
+        return a;
+    }
+};
+
+namespace aidax {
+
+static void collect_families(aidax_engine* e)
+{
+    struct Src { const KernelVariant* v; int n; };
+    const Src srcs[] = {
+        {kVariantsH0, kNumVariantsH0},   {kVariantsH8, kNumVariantsH8},   {kVariantsH12, kNumVariantsH12},
+        {kVariantsH16, kNumVariantsH16}, {kVariantsH20, kNumVariantsH20}, {kVariantsH24, kNumVariantsH24},
+        {kVariantsH32, kNumVariantsH32}, {kVariantsH40, kNumVariantsH40}, {kVariantsH64, kNumVariantsH64},
+        {kVariantsH80, kNumVariantsH80},
+    };
+    for (const Src& s : srcs)
+        for (int i = 0; i < s.n; ++i) {
+            const KernelVariant* kv = &s.v[i];
+            Family* fam = nullptr;
+            for (Family& f : e->families)
+                if (f.cell == kv->cell && (kv->cell == 2 || f.H == kv->H)) fam = &f;
+            if (!fam) { e->families.push_back(Family{kv->cell, kv->H, {}}); fam = &e->families.back(); }
+            fam->variants.push_back(kv);
+        }
+    for (Family& f : e->families)
+        std::stable_sort(f.variants.begin(), f.variants.end(), [](const KernelVariant* a, const KernelVariant* b) { return a->ws < b->ws; });
+}
+
+static void mark_ctrl(aidax_engine* e, int s) { e->dirty_ctrl[s] = 1; e->any_dirty = true; }
+
+static void write_coefs(aidax_engine* e, int s, uint32_t mask)
+{
+    const StreamHost& sh = e->streams[s];
+    for (int b = 0; b < kNumBiquads; ++b) {
+        if (!((mask >> b) & 1u)) continue;
+        const BiquadCoef& c = sh.bq[b];
+        const double v[5] = {c.a0, c.a1, c.a2, c.b1, c.b2};
+        for (int i = 0; i < 5; ++i) e->h_bq_coef[(size_t)(b * 5 + i) * e->cap + s] = v[i];
+    }
+    e->dirty_coef[s] = 1;
+    e->any_dirty = true;
+}
+
+static void sync_stream_shadow(aidax_engine* e, int s)
+{
+    const StreamHost& sh = e->streams[s];
+    e->h_flags[s] = sh.flags;
+    e->h_pre_target[s] = sh.pre_target;
+    e->h_master_target[s] = sh.master_target;
+    e->h_p_port[s] = sh.ctrl[AIDAX_CTRL_PARAM1];
+    e->h_p_port[(size_t)e->cap + s] = sh.ctrl[AIDAX_CTRL_PARAM2];
+    mark_ctrl(e, s);
+}
+
+// upload [lo, hi) of a per-stream array with `rows` rows of pitch cap
+template <typename T>
+static cudaError_t upload_rows(aidax_engine* e, T* dev, const T* host, int rows, int lo, int hi)
+{
+    if (hi <= lo) return cudaSuccess;
+    if (rows == 1) return cudaMemcpyAsync(dev + lo, host + lo, (size_t)(hi - lo) * sizeof(T), cudaMemcpyHostToDevice, e->stream);
+    return cudaMemcpy2DAsync(dev + lo, (size_t)e->cap * sizeof(T), host + lo, (size_t)e->cap * sizeof(T), (size_t)(hi - lo) * sizeof(T),
+                             rows, cudaMemcpyHostToDevice, e->stream);
+}
+
+static int upload_dirty(aidax_engine* e, int first, int n)
+{
+    if (e->models_dirty) {
+        std::vector<ModelDev> md(e->models.size());
+        for (size_t i = 0; i < e->models.size(); ++i) {
+            const ModelEntry& m = e->models[i];
+            md[i] = ModelDev{m.d_weights, m.host.desc.in_gain, m.host.desc.out_gain, m.host.desc.in_skip, m.host.desc.input_size};
+        }
+        if (e->d_models.n < md.size()) {
+            e->d_models.release();
+            CUDA_TRY(e->d_models.alloc(std::max<size_t>(md.size() * 2, 64)));
+        }
+        CUDA_TRY(cudaMemcpy(e->d_models.d, md.data(), md.size() * sizeof(ModelDev), cudaMemcpyHostToDevice));
+        e->models_dirty = false;
+    }
+    if (!e->any_dirty) return AIDAX_OK;
+    const int last = std::min(first + n, e->n_open_hi);
+    int clo = last, chi = first, flo = last, fhi = first, mlo = last, mhi = first;
+    bool remaining = false;
+    for (int s = first; s < last; ++s) {
+        if (e->dirty_ctrl[s]) { clo = std::min(clo, s); chi = s + 1; e->dirty_ctrl[s] = 0; }
+        if (e->dirty_coef[s]) { flo = std::min(flo, s); fhi = s + 1; e->dirty_coef[s] = 0; }
+        if (e->dirty_cmd[s]) { mlo = std::min(mlo, s); mhi = s + 1; e->dirty_cmd[s] = 0; }
+    }
+    if (first > 0 || last < e->n_open_hi) {
+        for (int s = 0; s < e->n_open_hi && !remaining; ++s)
+            if ((s < first || s >= last) && (e->dirty_ctrl[s] || e->dirty_coef[s] || e->dirty_cmd[s])) remaining = true;
+    }
+    e->any_dirty = remaining;
+    CUDA_TRY(upload_rows(e, e->d_flags.d, e->h_flags.data(), 1, clo, chi));
+    CUDA_TRY(upload_rows(e, e->d_pre_target.d, e->h_pre_target.data(), 1, clo, chi));
+    CUDA_TRY(upload_rows(e, e->d_master_target.d, e->h_master_target.data(), 1, clo, chi));
+    CUDA_TRY(upload_rows(e, e->d_p_port.d, e->h_p_port.data(), 2, clo, chi));
+    CUDA_TRY(upload_rows(e, e->d_bq_coef.d, e->h_bq_coef.data(), kNumBiquads * 5, flo, fhi));
+    if (mhi > mlo) {
+        // Commands for streams outside [mlo, mhi) of this upload keep their device copy: the device
+        // clears a command when it executes it, and the host clears its shadow after uploading it.
+        CUDA_TRY(upload_rows(e, e->d_cmd.d, e->h_cmd.data(), 1, mlo, mhi));
+        CUDA_TRY(upload_rows(e, e->d_p_init.d, e->h_p_init.data(), 2, mlo, mhi));
+        CUDA_TRY(upload_rows(e, e->d_cmd_pre_mem.d, e->h_cmd_pre_mem.data(), 1, mlo, mhi));
+        CUDA_TRY(upload_rows(e, e->d_cmd_master_mem.d, e->h_cmd_master_mem.data(), 1, mlo, mhi));
+        CUDA_TRY(upload_rows(e, e->d_exp_coef.d, e->h_exp_coef.data(), 1, mlo, mhi));
+        CUDA_TRY(upload_rows(e, e->d_lin_denom.d, e->h_lin_denom.data(), 1, mlo, mhi));
+        // pageable host memory: the async copies above are staged before returning, so the shadow can be cleared
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        for (int s = mlo; s < mhi; ++s) e->h_cmd[s] = 0;
+    }
+    return AIDAX_OK;
+}
+
+static const KernelVariant* choose_variant(const aidax_engine* e, const Family& fam, int n_streams)
+{
+    const auto& v = fam.variants;
+    if (v.size() == 1) return v[0];
+    if (e->tile_mode == 1) return v.front();
+    if (e->tile_mode == 2) return v.back();
+    // auto: the widest tile that still gives every SM at least 4 warps; otherwise trade FFMA
+    // efficiency for parallelism (fewer streams per warp).
+    const int want_warps = e->sm_count * 4;
+    for (int i = (int)v.size() - 1; i > 0; --i)
+        if ((n_streams + v[i]->ws - 1) / v[i]->ws >= want_warps) return v[i];
+    return v.front();
+}
+
+static int build_plan(aidax_engine* e, int first, int n)
+{
+    if (e->plan_epoch == e->membership_epoch && e->plan_first == first && e->plan_n == n && e->plan_tile_mode == e->tile_mode) return AIDAX_OK;
+    e->plan.clear();
+    e->h_tables.clear();
+    const int last = std::min(first + n, e->n_open_hi);
+    for (const Family& fam : e->families) {
+        // gather (model, slot) pairs of this family, grouped by model
+        std::map<int, std::vector<int>> by_model;
+        int total = 0;
+        for (int s = first; s < last; ++s) {
+            const StreamHost& sh = e->streams[s];
+            if (!sh.open) continue;
+            if (fam.cell == 2) {
+                if (sh.model < 0) { by_model[-1].push_back(s); ++total; }
+            } else if (sh.model >= 0) {
+                const aidax_model_desc& d = e->models[sh.model].host.desc;
+                if (d.cell == fam.cell && d.hidden == fam.H) { by_model[sh.model].push_back(s); ++total; }
+            }
+        }
+        if (!total) continue;
+        LaunchPlan lp;
+        lp.kv = choose_variant(e, fam, total);
+        const int CS = lp.kv->ws * lp.kv->NW;
+        std::vector<int> blk_model, blk_slots;
+        for (auto& kv : by_model) {
+            const std::vector<int>& slots = kv.second;
+            if (kv.first >= 0) lp.max_param_tiles = std::max(lp.max_param_tiles, e->models[kv.first].host.desc.input_size - 1);
+            for (size_t off = 0; off < slots.size(); off += CS) {
+                blk_model.push_back(std::max(kv.first, 0));
+                for (int j = 0; j < CS; ++j) blk_slots.push_back(off + j < slots.size() ? slots[off + j] : -1);
+            }
+        }
+        lp.n_blocks = (int)blk_model.size();
+        lp.tbl_offset_model = e->h_tables.size();
+        e->h_tables.insert(e->h_tables.end(), blk_model.begin(), blk_model.end());
+        lp.tbl_offset_slots = e->h_tables.size();
+        e->h_tables.insert(e->h_tables.end(), blk_slots.begin(), blk_slots.end());
+        e->plan.push_back(lp);
+    }
+    if (e->d_tables.n < e->h_tables.size()) {
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        e->d_tables.release();
+        CUDA_TRY(e->d_tables.alloc(e->h_tables.size() * 2 + 1024));
+    }
+    if (!e->h_tables.empty()) {
+        CUDA_TRY(cudaStreamSynchronize(e->stream)); // a previous launch may still read the old table
+        CUDA_TRY(cudaMemcpy(e->d_tables.d, e->h_tables.data(), e->h_tables.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    e->plan_epoch = e->membership_epoch;
+    e->plan_first = first;
+    e->plan_n = n;
+    e->plan_tile_mode = e->tile_mode;
+    return AIDAX_OK;
+}
+
+static int launch_all(aidax_engine* e, int first, int n, int n_samples, const float* d_in, float* d_out, int layout, size_t stride)
+{
+    int rc = upload_dirty(e, first, n);
+    if (rc) return rc;
+    rc = build_plan(e, first, n);
+    if (rc) return rc;
+    for (const LaunchPlan& lp : e->plan) {
+        const KernelVariant* kv = lp.kv;
+        const int weights_floats = kv->cell == 2 ? 0 : packed_weight_floats(kv->H);
+        // samples per shared-memory sub-block: as many as fit with >= 2 CTAs per SM, capped at the period
+        int ts = n_samples;
+        const size_t budget = e->smem_optin / 2 - 1024;
+        auto smem_for = [&](int t) { return (size_t)(weights_floats + kv->NW * kv->warp_smem_floats(t, lp.max_param_tiles)) * sizeof(float); };
+        while (ts > 8 && smem_for(ts) > budget) ts = (ts + 1) / 2;
+        if (smem_for(ts) > e->smem_optin) return fail(AIDAX_ERR_CAPACITY, "kernel variant needs %zu B shared memory", smem_for(ts));
+        const size_t smem = smem_for(ts);
+        const void* fn = kv->fn[e->math_mode ? 1 : 0];
+        if (std::find(e->attr_done.begin(), e->attr_done.end(), fn) == e->attr_done.end()) {
+            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_optin));
+            e->attr_done.push_back(fn);
+        }
+        RenderParams p{};
+        p.in = d_in; p.out = d_out; p.layout = layout; p.stride = (long long)stride; p.first_stream = first;
+        p.n_samples = n_samples; p.ts = ts; p.math_mode = e->math_mode;
+        p.blk_model = e->d_tables.d + lp.tbl_offset_model;
+        p.blk_slots = e->d_tables.d + lp.tbl_offset_slots;
+        p.models = e->d_models.d;
+        p.sa = e->sa();
+        void* args[] = {&p};
+        CUDA_TRY(cudaLaunchKernel(fn, dim3(lp.n_blocks), dim3(kv->NW * 32), args, smem, e->stream));
+        e->launches++;
+    }
+    return AIDAX_OK;
+}
+
+static int check_stream(aidax_engine* e, int s)
+{
+    if (!e) return fail(AIDAX_ERR_ARG, "null engine");
+    if (s < 0 || s >= e->n_open_hi || !e->streams[s].open) return fail(AIDAX_ERR_ARG, "unknown stream %d", s);
+    return AIDAX_OK;
+}
+
+} // namespace aidax
+
+// ================================================================================ C ABI
+extern "C" {
+
+const char* aidax_last_error(void) { return g_last_error.c_str(); }
+int aidax_abi_version(void) { return AIDAX_ABI_VERSION; }
+
+int aidax_engine_create(int device, int max_streams, int max_block, aidax_engine** out)
+{
+    if (!out || max_streams <= 0 || max_block <= 0) return fail(AIDAX_ERR_ARG, "bad engine_create arguments");
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return fail(AIDAX_ERR_CUDA, "no CUDA device available (the engine has no CPU fallback)");
+    if (device < 0 || device >= n_dev) return fail(AIDAX_ERR_ARG, "device %d out of range (%d devices)", device, n_dev);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(AIDAX_ERR_CUDA, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
+    std::unique_ptr<aidax_engine> e(new aidax_engine());
+    e->device = device;
+    e->cap = (max_streams + 31) & ~31;
+    e->max_block = max_block;
+    e->sm_count = prop.multiProcessorCount;
+    e->smem_optin = prop.sharedMemPerBlockOptin;
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    const size_t cap = (size_t)e->cap;
+    e->streams.resize(cap);
+    e->dirty_ctrl.assign(cap, 0); e->dirty_coef.assign(cap, 0); e->dirty_cmd.assign(cap, 0);
+    e->h_flags.assign(cap, 0); e->h_cmd.assign(cap, 0);
+    e->h_pre_target.assign(cap, 0.f); e->h_master_target.assign(cap, 0.f);
+    e->h_p_port.assign(2 * cap, 0.f); e->h_p_init.assign(2 * cap, 0.f);
+    e->h_cmd_pre_mem.assign(cap, 0.f); e->h_cmd_master_mem.assign(cap, 0.f);
+    e->h_exp_coef.assign(cap, 0.f); e->h_lin_denom.assign(cap, 4800.f);
+    e->h_bq_coef.assign((size_t)kNumBiquads * 5 * cap, 0.0);
+    CUDA_TRY(e->d_flags.alloc(cap)); CUDA_TRY(e->d_cmd.alloc(cap)); CUDA_TRY(e->d_dflags.alloc(cap));
+    CUDA_TRY(e->d_pre_target.alloc(cap)); CUDA_TRY(e->d_master_target.alloc(cap));
+    CUDA_TRY(e->d_p_port.alloc(2 * cap)); CUDA_TRY(e->d_p_init.alloc(2 * cap));
+    CUDA_TRY(e->d_cmd_pre_mem.alloc(cap)); CUDA_TRY(e->d_cmd_master_mem.alloc(cap));
+    CUDA_TRY(e->d_exp_coef.alloc(cap)); CUDA_TRY(e->d_lin_denom.alloc(cap));
+    CUDA_TRY(e->d_pre_mem.alloc(cap)); CUDA_TRY(e->d_master_mem.alloc(cap));
+    CUDA_TRY(e->d_p_mem.alloc(2 * cap)); CUDA_TRY(e->d_p_step.alloc(2 * cap)); CUDA_TRY(e->d_p_target.alloc(2 * cap));
+    CUDA_TRY(e->d_rnn.alloc((size_t)2 * kMaxHidden * cap));
+    CUDA_TRY(e->d_bq_coef.alloc((size_t)kNumBiquads * 5 * cap)); CUDA_TRY(e->d_bq_z.alloc((size_t)kNumBiquads * 2 * cap));
+    CUDA_TRY(e->d_io_in.alloc(cap * (size_t)max_block)); CUDA_TRY(e->d_io_out.alloc(cap * (size_t)max_block));
+    collect_families(e.get());
+    *out = e.release();
+    return AIDAX_OK;
+}
+
+int aidax_engine_destroy(aidax_engine* e)
+{
+    if (!e) return AIDAX_OK;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    for (ModelEntry& m : e->models) if (m.d_weights) cudaFree(m.d_weights);
+    e->d_flags.release(); e->d_cmd.release(); e->d_dflags.release(); e->d_pre_target.release(); e->d_master_target.release();
+    e->d_p_port.release(); e->d_p_init.release(); e->d_cmd_pre_mem.release(); e->d_cmd_master_mem.release();
+    e->d_exp_coef.release(); e->d_lin_denom.release(); e->d_pre_mem.release(); e->d_master_mem.release();
+    e->d_p_mem.release(); e->d_p_step.release(); e->d_p_target.release(); e->d_rnn.release();
+    e->d_bq_coef.release(); e->d_bq_z.release(); e->d_io_in.release(); e->d_io_out.release();
+    e->d_models.release(); e->d_tables.release();
+    cudaStreamDestroy(e->stream);
+    delete e;
+    return AIDAX_OK;
+}
+
+void* aidax_engine_cuda_stream(aidax_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+int aidax_engine_configure(aidax_engine* e, int tile_mode, int math_mode)
+{
+    if (!e || tile_mode < 0 || tile_mode > 2 || math_mode < 0 || math_mode > 1) return fail(AIDAX_ERR_ARG, "bad configure arguments");
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->tile_mode = tile_mode;
+    e->math_mode = math_mode;
+    return AIDAX_OK;
+}
+
+static int register_host_model(aidax_engine* e, HostModel&& hm, int* id_out)
+{
+    const std::vector<float> packed = pack_model(hm);
+    ModelEntry me;
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaMalloc((void**)&me.d_weights, packed.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(me.d_weights, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+    me.host = std::move(hm);
+    e->models.push_back(std::move(me));
+    e->models_dirty = true;
+    if (id_out) *id_out = (int)e->models.size() - 1;
+    return AIDAX_OK;
+}
+
+int aidax_model_register(aidax_engine* e, const aidax_model_desc* desc, const float* W, const float* U, const float* b,
+                         const float* dense_w, float dense_b, int* model_id_out)
+{
+    if (!e || !desc || !W || !U || !b || !dense_w) return fail(AIDAX_ERR_ARG, "null argument");
+    if (desc->cell != AIDAX_CELL_LSTM && desc->cell != AIDAX_CELL_GRU) return fail(AIDAX_ERR_MODEL, "unknown cell type %d", desc->cell);
+    if (!hidden_size_supported(desc->hidden)) return fail(AIDAX_ERR_MODEL, "hidden size %d is not in the variant table", desc->hidden);
+    if (desc->input_size < 1 || desc->input_size > kMaxInput) return fail(AIDAX_ERR_MODEL, "input_size %d not supported", desc->input_size);
+    const int H = desc->hidden, IN = desc->input_size, G = desc->cell == AIDAX_CELL_LSTM ? 4 : 3;
+    HostModel hm;
+    hm.desc = *desc;
+    hm.desc.in_skip = desc->in_skip != 0;
+    hm.W.assign(W, W + (size_t)IN * G * H);
+    hm.U.assign(U, U + (size_t)H * G * H);
+    hm.b.assign(b, b + (size_t)(desc->cell == AIDAX_CELL_LSTM ? 4 * H : 6 * H));
+    hm.dense_w.assign(dense_w, dense_w + H);
+    hm.dense_b = dense_b;
+    std::lock_guard<std::mutex> lk(e->mu);
+    return register_host_model(e, std::move(hm), model_id_out);
+}
+
+int aidax_model_load_json(aidax_engine* e, const char* path, int* model_id_out, int* input_size_out)
+{
+    if (!e || !path) return fail(AIDAX_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(e->mu);
+    auto it = e->model_cache.find(path);
+    int id = -1;
+    if (it != e->model_cache.end()) {
+        id = it->second;
+    } else {
+        HostModel hm;
+        try {
+            hm = load_model_file(path);
+        } catch (const std::exception& ex) {
+            return fail(AIDAX_ERR_MODEL, "Unable to load json file: %s Error: %s", path, ex.what());
+        }
+        const int rc = register_host_model(e, std::move(hm), &id);
+        if (rc) return rc;
+        e->model_cache[path] = id;
+    }
+    if (model_id_out) *model_id_out = id;
+    if (input_size_out) *input_size_out = e->models[id].host.desc.input_size;
+    return AIDAX_OK;
+}
+
+int aidax_model_describe(aidax_engine* e, int model_id, aidax_model_desc* out)
+{
+    if (!e || !out) return fail(AIDAX_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (model_id < 0 || model_id >= (int)e->models.size()) return fail(AIDAX_ERR_ARG, "unknown model %d", model_id);
+    *out = e->models[model_id].host.desc;
+    return AIDAX_OK;
+}
+
+int aidax_stream_open(aidax_engine* e, double sample_rate, int* stream_id_out)
+{
+    if (!e || !stream_id_out) return fail(AIDAX_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(e->mu);
+    int s = -1;
+    if (e->n_open_hi < e->cap) s = e->n_open_hi++;
+    else
+        for (int i = 0; i < e->cap; ++i)
+            if (!e->streams[i].open) { s = i; break; }
+    if (s < 0) return fail(AIDAX_ERR_CAPACITY, "all %d stream slots are in use", e->cap);
+    StreamHost& sh = e->streams[s];
+    init_stream_host(sh, sample_rate);
+    decode_controls(sh, sh.ctrl, /*loading=*/true, /*model_bound=*/false);
+    sh.have_ctrl = false;
+    sh.pre_target = 1.f; // instantiate: preGain target 1, master target 0 until the first run()
+    sh.master_target = 0.f;
+    sync_stream_shadow(e, s);
+    write_coefs(e, s, (1u << kNumBiquads) - 1u);
+    e->h_exp_coef[s] = exp_smoother_coef(sample_rate);
+    e->h_lin_denom[s] = 0.1f * 48000.0f;
+    e->h_cmd[s] = C_SET_GAIN_MEMS | C_ZERO_FILTERS;
+    e->h_cmd_pre_mem[s] = 1.f;
+    e->h_cmd_master_mem[s] = 0.f;
+    e->dirty_cmd[s] = 1;
+    e->any_dirty = true;
+    e->membership_epoch++;
+    *stream_id_out = s;
+    return AIDAX_OK;
+}
+
+int aidax_stream_close(aidax_engine* e, int stream)
+{
+    int rc = check_stream(e, stream);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->streams[stream].open = false;
+    e->streams[stream].model = -1;
+    e->membership_epoch++;
+    return AIDAX_OK;
+}
+
+int aidax_stream_activate(aidax_engine* e, int stream)
+{
+    int rc = check_stream(e, stream);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    StreamHost& sh = e->streams[stream];
+    e->h_cmd[stream] |= C_SET_GAIN_MEMS | (sh.model >= 0 ? C_FIRST_RUN : 0u);
+    e->h_cmd_pre_mem[stream] = sh.pre_target;
+    e->h_cmd_master_mem[stream] = sh.master_target;
+    e->dirty_cmd[stream] = 1;
+    e->any_dirty = true;
+    return AIDAX_OK;
+}
+
+int aidax_stream_set_model(aidax_engine* e, int stream, int model_id, float old_param1, float old_param2)
+{
+    int rc = check_stream(e, stream);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (model_id >= (int)e->models.size()) return fail(AIDAX_ERR_ARG, "unknown model %d", model_id);
+    StreamHost& sh = e->streams[stream];
+    sh.model = model_id < 0 ? -1 : model_id;
+    if (model_id >= 0) {
+        const aidax_model_desc& d = e->models[model_id].host.desc;
+        e->h_lin_denom[stream] = 0.1f * d.samplerate;
+        e->h_p_init[stream] = old_param1;
+        e->h_p_init[(size_t)e->cap + stream] = old_param2;
+        e->h_cmd[stream] |= C_SET_MODEL;
+        e->dirty_cmd[stream] = 1;
+        // the new model's smoother targets, as setTargetValue would leave them (ValueSmoother.hpp:209-216)
+        sh.param_target[0] = float_not_equal(0.f, old_param1) ? old_param1 : 0.f;
+        sh.param_target[1] = float_not_equal(0.f, old_param2) ? old_param2 : 0.f;
+    }
+    // F_NET depends on the binding
+    if (sh.have_ctrl) decode_controls(sh, sh.ctrl, sh.loading, sh.model >= 0);
+    else {
+        float c[AIDAX_N_CONTROLS];
+        std::memcpy(c, sh.ctrl, sizeof(c));
+        const float pt = sh.pre_target, mt = sh.master_target;
+        decode_controls(sh, c, sh.loading, sh.model >= 0);
+        sh.have_ctrl = false; sh.pre_target = pt; sh.master_target = mt;
+    }
+    sync_stream_shadow(e, stream);
+    e->any_dirty = true;
+    e->membership_epoch++;
+    return AIDAX_OK;
+}
+
+int aidax_stream_set_controls(aidax_engine* e, int stream, const float controls[AIDAX_N_CONTROLS], int loading)
+{
+    int rc = check_stream(e, stream);
+    if (rc) return rc;
+    if (!controls) return fail(AIDAX_ERR_ARG, "null controls");
+    std::lock_guard<std::mutex> lk(e->mu);
+    StreamHost& sh = e->streams[stream];
+    const uint32_t redesigned = decode_controls(sh, controls, loading != 0, sh.model >= 0);
+    if (redesigned) write_coefs(e, stream, redesigned);
+    sync_stream_shadow(e, stream);
+    return AIDAX_OK;
+}
+
+int aidax_streams_set_params(aidax_engine* e, int first_stream, int n, const float* p1, const float* p2)
+{
+    if (!e || n < 0 || first_stream < 0 || first_stream + n > e->n_open_hi) return fail(AIDAX_ERR_ARG, "bad stream range");
+    std::lock_guard<std::mutex> lk(e->mu);
+    for (int i = 0; i < n; ++i) {
+        const int s = first_stream + i;
+        StreamHost& sh = e->streams[s];
+        if (p1) { sh.ctrl[AIDAX_CTRL_PARAM1] = p1[i]; e->h_p_port[s] = p1[i]; }
+        if (p2) { sh.ctrl[AIDAX_CTRL_PARAM2] = p2[i]; e->h_p_port[(size_t)e->cap + s] = p2[i]; }
+        e->dirty_ctrl[s] = 1;
+    }
+    e->any_dirty = true;
+    return AIDAX_OK;
+}
+
+int aidax_stream_get_state(aidax_engine* e, int stream, float* h, float* c, double* biquad_z)
+{
+    int rc = check_stream(e, stream);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    const StreamHost& sh = e->streams[stream];
+    const size_t cap = (size_t)e->cap;
+    if (sh.model >= 0) {
+        const int H = e->models[sh.model].host.desc.hidden;
+        if (h) CUDA_TRY(cudaMemcpy2D(h, sizeof(float), e->d_rnn.d + stream, cap * sizeof(float), sizeof(float), H, cudaMemcpyDeviceToHost));
+        if (c) CUDA_TRY(cudaMemcpy2D(c, sizeof(float), e->d_rnn.d + (size_t)kMaxHidden * cap + stream, cap * sizeof(float), sizeof(float), H, cudaMemcpyDeviceToHost));
+    }
+    if (biquad_z)
+        CUDA_TRY(cudaMemcpy2D(biquad_z, sizeof(double), e->d_bq_z.d + stream, cap * sizeof(double), sizeof(double), kNumBiquads * 2, cudaMemcpyDeviceToHost));
+    return AIDAX_OK;
+}
+
+static int render_common_checks(aidax_engine* e, int first, int n, int n_samples, const void* in, void* out, int layout)
+{
+    if (!e) return fail(AIDAX_ERR_ARG, "null engine");
+    if (first < 0 || n < 0 || first + n > e->cap) return fail(AIDAX_ERR_ARG, "bad stream range [%d, %d)", first, first + n);
+    if (n_samples < 0 || n_samples > e->max_block) return fail(AIDAX_ERR_CAPACITY, "n_samples %d exceeds max_block %d", n_samples, e->max_block);
+    if (n_samples > 0 && n > 0 && (!in || !out)) return fail(AIDAX_ERR_ARG, "null audio buffer");
+    if (layout != AIDAX_LAYOUT_PLANAR && layout != AIDAX_LAYOUT_INTERLEAVED) return fail(AIDAX_ERR_ARG, "unknown layout %d", layout);
+    return AIDAX_OK;
+}
+
+static void after_render(aidax_engine* e, int first, int n, int n_samples)
+{
+    const int last = std::min(first + n, e->n_open_hi);
+    for (int s = first; s < last; ++s)
+        if (e->streams[s].open) track_param_targets(e->streams[s], n_samples);
+}
+
+int aidax_render_device(aidax_engine* e, int first_stream, int n_streams, int n_samples, const float* d_in, float* d_out,
+                        int layout, size_t stride)
+{
+    int rc = render_common_checks(e, first_stream, n_streams, n_samples, d_in, d_out, layout);
+    if (rc) return rc;
+    if (n_samples == 0 || n_streams == 0) return AIDAX_OK; // run() with 0 samples is a legal no-op for audio (:606-609)
+    std::lock_guard<std::mutex> lk(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    rc = launch_all(e, first_stream, n_streams, n_samples, d_in, d_out, layout, stride);
+    if (rc) return rc;
+    after_render(e, first_stream, n_streams, n_samples);
+    return AIDAX_OK;
+}
+
+int aidax_render_host(aidax_engine* e, int first_stream, int n_streams, int n_samples, const float* in, float* out,
+                      int layout, size_t stride)
+{
+    int rc = render_common_checks(e, first_stream, n_streams, n_samples, in, out, layout);
+    if (rc) return rc;
+    if (n_samples == 0 || n_streams == 0) return AIDAX_OK;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    // Stage through the engine's device arena with a dense pitch (planar: n_samples, interleaved: n_streams)
+    const size_t rows = layout == AIDAX_LAYOUT_PLANAR ? (size_t)n_streams : (size_t)n_samples;
+    const size_t cols = layout == AIDAX_LAYOUT_PLANAR ? (size_t)n_samples : (size_t)n_streams;
+    if (stride < cols) return fail(AIDAX_ERR_ARG, "stride %zu smaller than row length %zu", stride, cols);
+    CUDA_TRY(cudaMemcpy2DAsync(e->d_io_in.d, cols * sizeof(float), in, stride * sizeof(float), cols * sizeof(float), rows,
+                               cudaMemcpyHostToDevice, e->stream));
+    rc = launch_all(e, first_stream, n_streams, n_samples, e->d_io_in.d, e->d_io_out.d, layout, cols);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(out, stride * sizeof(float), e->d_io_out.d, cols * sizeof(float), cols * sizeof(float), rows,
+                               cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    after_render(e, first_stream, n_streams, n_samples);
+    return AIDAX_OK;
+}
+
+int aidax_engine_synchronize(aidax_engine* e)
+{
+    if (!e) return fail(AIDAX_ERR_ARG, "null engine");
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return AIDAX_OK;
+}
+
+void* aidax_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        fail(AIDAX_ERR_CUDA, "cudaHostAlloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+void aidax_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+uint64_t aidax_engine_launch_count(aidax_engine* e) { return e ? e->launches : 0; }
+
+} // extern "C"

@@ -1,0 +1,53 @@
+// variants.cu -- explicit instantiations of chain_kernel for one hidden size (AIDAX_VARIANT_H).
+// Tile shapes (L lanes per stream group, S streams per group) per hidden size: the first entry is
+// the low-latency shape (one stream per group, many lanes), the last the throughput shape
+// (register tile of S streams x 4U gate rows per lane, >= 10 FFMA per 128-bit shared load).
+#include "kernels.cuh"
+#include "variants.h"
+
+#ifndef AIDAX_VARIANT_H
+#error "compile with -DAIDAX_VARIANT_H=<hidden size>"
+#endif
+
+namespace aidax {
+
+template <int H, int L, int S>
+static int wsf(int ts, int np) { return Tile<0, H, L, S>::warp_smem_floats(ts, np); }
+
+#define V(CELL, Hh, Ll, Ss, NWw)                                                                         \
+    { CELL, Hh, Ll, Ss, NWw, (32 / Ll) * Ss,                                                             \
+      { (const void*)&chain_kernel<CELL, Hh, Ll, Ss, NWw, 0>, (const void*)&chain_kernel<CELL, Hh, Ll, Ss, NWw, 1> }, \
+      &wsf<Hh, Ll, Ss> }
+#define BOTH(Hh, Ll, Ss, NWw) V(0, Hh, Ll, Ss, NWw), V(1, Hh, Ll, Ss, NWw)
+
+#define CAT_(a, b) a##b
+#define CAT(a, b) CAT_(a, b)
+
+const KernelVariant CAT(kVariantsH, AIDAX_VARIANT_H)[] = {
+#if AIDAX_VARIANT_H == 0
+    V(2, 8, 8, 8, 4),
+#elif AIDAX_VARIANT_H == 8
+    BOTH(8, 8, 1, 4), BOTH(8, 8, 4, 4), BOTH(8, 8, 8, 4),
+#elif AIDAX_VARIANT_H == 12
+    BOTH(12, 4, 1, 4), BOTH(12, 4, 2, 4), BOTH(12, 4, 4, 4),
+#elif AIDAX_VARIANT_H == 16
+    BOTH(16, 16, 1, 4), BOTH(16, 16, 4, 4), BOTH(16, 8, 8, 4),
+#elif AIDAX_VARIANT_H == 20
+    BOTH(20, 4, 1, 4), BOTH(20, 4, 2, 4), BOTH(20, 4, 4, 4),
+#elif AIDAX_VARIANT_H == 24
+    BOTH(24, 8, 1, 4), BOTH(24, 8, 4, 4), BOTH(24, 8, 8, 4),
+#elif AIDAX_VARIANT_H == 32
+    BOTH(32, 32, 1, 4), BOTH(32, 16, 4, 4), BOTH(32, 8, 4, 4),
+#elif AIDAX_VARIANT_H == 40
+    BOTH(40, 8, 1, 4), BOTH(40, 8, 2, 4), BOTH(40, 8, 4, 4),
+#elif AIDAX_VARIANT_H == 64
+    BOTH(64, 32, 1, 4), BOTH(64, 32, 4, 4), BOTH(64, 16, 4, 4),
+#elif AIDAX_VARIANT_H == 80
+    BOTH(80, 16, 1, 4), BOTH(80, 16, 2, 4), BOTH(80, 16, 4, 4),
+#else
+#error "unsupported hidden size"
+#endif
+};
+const int CAT(kNumVariantsH, AIDAX_VARIANT_H) = (int)(sizeof(CAT(kVariantsH, AIDAX_VARIANT_H)) / sizeof(KernelVariant));
+
+} // namespace aidax
