@@ -634,6 +634,25 @@ int aidax_stream_get_state(aidax_engine* e, int stream, float* h, float* c, doub
     return AIDAX_OK;
 }
 
+int aidax_stream_set_state(aidax_engine* e, int stream, const float* h, const float* c, const double* biquad_z)
+{
+    int rc = check_stream(e, stream);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    const StreamHost& sh = e->streams[stream];
+    const size_t cap = (size_t)e->cap;
+    if (sh.model >= 0) {
+        const int H = e->models[sh.model].host.desc.hidden;
+        if (h) CUDA_TRY(cudaMemcpy2D(e->d_rnn.d + stream, cap * sizeof(float), h, sizeof(float), sizeof(float), H, cudaMemcpyHostToDevice));
+        if (c) CUDA_TRY(cudaMemcpy2D(e->d_rnn.d + (size_t)kMaxHidden * cap + stream, cap * sizeof(float), c, sizeof(float), sizeof(float), H, cudaMemcpyHostToDevice));
+    }
+    if (biquad_z)
+        CUDA_TRY(cudaMemcpy2D(e->d_bq_z.d + stream, cap * sizeof(double), biquad_z, sizeof(double), sizeof(double), kNumBiquads * 2, cudaMemcpyHostToDevice));
+    return AIDAX_OK;
+}
+
 static int render_common_checks(aidax_engine* e, int first, int n, int n_samples, const void* in, void* out, int layout)
 {
     if (!e) return fail(AIDAX_ERR_ARG, "null engine");

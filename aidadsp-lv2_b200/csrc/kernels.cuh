@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(NW * 32) chain_kernel(const __grid_constant__ 
         if (tslot[s] >= 0) valid_mask |= 1u << s;
         else tslot[s] = 0;
     }
-    if (valid_mask == 0 && __all_sync(0xffffffffu, cslot < 0)) return; // whole warp empty
+    if (__all_sync(0xffffffffu, cslot < 0)) return; // whole warp empty (no slot in the warp's table)
 
     // ---- commands (open / activate / model swap) and the pre-warm they may request
     uint32_t cmd = 0;

@@ -71,6 +71,7 @@ def load_library():
     lib.aidax_stream_set_controls.argtypes = [vp, C.c_int, fp, C.c_int]
     lib.aidax_streams_set_params.argtypes = [vp, C.c_int, C.c_int, fp, fp]
     lib.aidax_stream_get_state.argtypes = [vp, C.c_int, fp, fp, C.POINTER(C.c_double)]
+    lib.aidax_stream_set_state.argtypes = [vp, C.c_int, fp, fp, C.POINTER(C.c_double)]
     lib.aidax_render_host.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_size_t]
     lib.aidax_render_device.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_size_t]
     lib.aidax_engine_synchronize.argtypes = [vp]
@@ -197,6 +198,13 @@ class Engine:
         z = np.zeros(14, dtype=np.float64)
         self._chk(self.lib.aidax_stream_get_state(self.h, s, _fptr(h), _fptr(c), z.ctypes.data_as(C.POINTER(C.c_double))))
         return h, c, z
+
+    def set_state(self, s, h=None, c=None, z=None):
+        h = np.ascontiguousarray(h, dtype=np.float32) if h is not None else None
+        c = np.ascontiguousarray(c, dtype=np.float32) if c is not None else None
+        z = np.ascontiguousarray(z, dtype=np.float64) if z is not None else None
+        self._chk(self.lib.aidax_stream_set_state(self.h, s, _fptr(h) if h is not None else None, _fptr(c) if c is not None else None,
+                                                  z.ctypes.data_as(C.POINTER(C.c_double)) if z is not None else None))
 
     # -- render
     def render_host(self, x, out=None, first=0, layout=LAYOUT_PLANAR):

@@ -161,6 +161,9 @@ int aidax_streams_set_params(aidax_engine* e, int first_stream, int n, const flo
 /* Test/debug observability: copy the recurrent state (h[hidden], c[hidden]; c only for LSTM) and
  * the 7x2 biquad states (order: in_lpf, depth, bass, mid, treble, presence, dc) of a stream. */
 int aidax_stream_get_state(aidax_engine* e, int stream, float* h, float* c, double* biquad_z);
+/* Inverse of get_state (NULL = leave as is): checkpoint/restore of the DSP state, which the reference
+ * never persists (LV2 state only stores the model path, rt-neural-generic.cpp:763-796).  Synchronises. */
+int aidax_stream_set_state(aidax_engine* e, int stream, const float* h, const float* c, const double* biquad_z);
 
 /* ------------------------------------------------------------------ render ---- */
 

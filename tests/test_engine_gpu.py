@@ -1,0 +1,114 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle and the reference's
+own golden vectors.  Tolerances: 1e-5 on the bundled 2048-sample vectors (the reference's own
+TEST_MODEL_THR, rt-neural-generic.h:182); 1e-4 max-abs for longer runs (BASELINE.json north_star);
+bit-exact for the filter/gain chain with the network bypassed."""
+import numpy as np
+import pytest
+
+import aidadsp_lv2_b200 as ax
+from aidadsp_lv2_b200 import models, signals
+from oracle import pyoracle
+
+pytestmark = pytest.mark.gpu
+
+T = 128
+
+
+def _model_only_controls(**kw):
+    return ax.default_controls(ANTIALIASING=0.0, DCBLOCKER=0.0, EQBYPASS=1.0, **kw)
+
+
+@pytest.mark.parametrize("tile_mode", [1, 2])
+def test_bundled_golden_vectors(native_libs, bundled_models, tile_mode):
+    eng = ax.Engine(max_streams=64, max_block=2048)
+    eng.configure(tile_mode=tile_mode, math_mode=0)
+    ms = [models.load_json(p) for p in bundled_models]
+    sids = []
+    for p in bundled_models:
+        mid, insz = eng.load_json(p)
+        assert insz == 1
+        s = eng.open_stream()
+        eng.set_model(s, mid)
+        eng.set_controls(s, _model_only_controls(), loading=False)
+        sids.append(s)
+    n = len(sids)
+    eng.render_host(np.zeros((n, T), dtype=np.float32))  # executes open/model commands incl. the pre-warm
+    for s, m in zip(sids, ms):
+        z = np.zeros(m.hidden, dtype=np.float32)
+        eng.set_state(s, h=z, c=z)  # golden vectors start from reset() (testModel, rt-neural-generic.cpp:900-955)
+        eng.activate(s)             # gain smoothers jump to 1.0
+    x = np.stack([m.input_batch for m in ms])
+    y = eng.render_host(x)
+    for i, m in enumerate(ms):
+        err = np.abs(y[i] - m.output_batch).max()
+        assert err <= 1e-5, (bundled_models[i], err)
+        yo = pyoracle.OracleModel(m).forward(m.input_batch)
+        assert np.abs(y[i] - yo).max() <= 1e-5
+    eng.close()
+
+
+def _run_chain_pair(eng, m, controls_list, n_buffers, x, math_mode=0, loading_first=True):
+    """Runs len(controls_list) streams through engine and oracle; returns (engine_out, oracle_out)."""
+    n = len(controls_list)
+    mid = eng.register_model(m) if m is not None else -1
+    sids, orcs = [], []
+    for c in controls_list:
+        s = eng.open_stream()
+        o = pyoracle.OracleStream()
+        if m is not None:
+            eng.set_model(s, mid)
+            o.set_model(m)
+        eng.set_controls(s, c, loading=False)
+        o.set_loading(False)
+        sids.append(s)
+        orcs.append(o)
+    first = sids[0]
+    ye = np.empty_like(x)
+    yo = np.empty_like(x)
+    for b in range(n_buffers):
+        sl = slice(b * T, (b + 1) * T)
+        ye[:, sl] = eng.render_host(np.ascontiguousarray(x[:, sl]), first=first)
+        for i, o in enumerate(orcs):
+            yo[i, sl] = o.run(controls_list[i], x[i, sl])
+    return ye, yo
+
+
+def test_chain_only_bit_exact(native_libs):
+    """No model bound: filters + smoothers must equal the reference arithmetic bit for bit."""
+    eng = ax.Engine(max_streams=64, max_block=T)
+    cl = [
+        ax.default_controls(),
+        ax.default_controls(EQPOS=1.0, BASS=3.0, MID=-2.0, TREBLE=4.0, DEPTH=1.0, PRESENCE=2.0, PREGAIN=6.0, MASTER=-3.0),
+        ax.default_controls(EQPOS=0.0, BASS=-8.0, MID=8.0, MIDQ=2.5, TREBLE=-4.0, DEPTH=-1.0, PRESENCE=-2.0, ANTIALIASING=0.0),
+        ax.default_controls(MTYPE=1.0, MID=5.0, MFREQ=1200.0, DCBLOCKER=0.0, ANTIALIASING=100.0),
+        ax.default_controls(EQBYPASS=1.0, PREGAIN=-12.0, MASTER=15.0),
+        ax.default_controls(ENABLED=0.0),
+    ]
+    x = signals.sweep_noise_block(len(cl), 20 * T)
+    ye, yo = _run_chain_pair(eng, None, cl, 20, x)
+    assert np.array_equal(ye, yo), np.abs(ye - yo).max()
+    assert np.array_equal(ye[5], x[5])  # disabled = straight copy
+    eng.close()
+
+
+@pytest.mark.parametrize("cell,hidden,input_size", [(0, 16, 1), (1, 16, 3), (0, 40, 1), (1, 8, 2), (0, 12, 2), (1, 24, 1), (0, 20, 3), (1, 32, 1), (0, 64, 1), (1, 80, 1)])
+@pytest.mark.parametrize("tile_mode", [1, 2])
+def test_full_chain_vs_oracle(native_libs, cell, hidden, input_size, tile_mode):
+    eng = ax.Engine(max_streams=64, max_block=T)
+    eng.configure(tile_mode=tile_mode, math_mode=0)
+    m = models.synthetic(cell, hidden, input_size, seed=1000 + hidden + input_size, in_skip=input_size % 2, in_gain_db=-3.0, out_gain_db=2.0)
+    cl = [
+        ax.default_controls(EQPOS=1.0, BASS=3.0, MID=-2.0, TREBLE=4.0, DEPTH=1.0, PRESENCE=2.0, PARAM1=0.3, PARAM2=0.8),
+        ax.default_controls(EQPOS=0.0, BASS=3.0, MID=-2.0, TREBLE=4.0, DEPTH=1.0, PRESENCE=2.0, PARAM1=0.9, PARAM2=0.1),
+        ax.default_controls(NETBYPASS=1.0),
+        ax.default_controls(EQBYPASS=1.0, PREGAIN=3.0, PARAM1=0.5),
+        ax.default_controls(ENABLED=0.0),
+    ]
+    n_buf = 24
+    x = signals.sweep_noise_block(len(cl), n_buf * T)
+    ye, yo = _run_chain_pair(eng, m, cl, n_buf, x)
+    err = np.abs(ye - yo).max(axis=1)
+    assert err.max() <= 1e-4, err
+    assert np.array_equal(ye[2], yo[2])  # network bypassed -> bit exact
+    assert np.array_equal(ye[4], x[4])
+    eng.close()
