@@ -7,4 +7,5 @@ synthetic signals.  It never computes audio itself and has no CPU fallback.
 """
 from .build import build, lib_path, LIB_DIR, PKG_DIR  # noqa: F401
 from .engine import Engine, AidaxError, CTRL, N_CONTROLS, default_controls, LAYOUT_PLANAR, LAYOUT_INTERLEAVED  # noqa: F401
-from . import models, signals  # noqa: F401
+from . import models, signals, sharding  # noqa: F401
+from .host import BatchHost, plugin_path, PORT  # noqa: F401

@@ -1,0 +1,527 @@
+// batch_host.cpp -- libaidax_host.so: a minimal, multi-instance LV2 host for rt-neural-generic
+// binaries (see include/aidax_host.h).  No CUDA here: the GPU is reached only through the plugin.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/aidax_batch.h"
+#include "../../include/aidax_host.h"
+#include "../../include/aidax_lv2_abi.h"
+
+namespace {
+
+thread_local std::string g_err;
+void set_err(const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+constexpr int kPortCount = 25;  // ttl/rt-neural-generic.ttl: ports 0..24
+constexpr int kPortIn = 0, kPortOut = 1, kPortControl = 2, kPortNotify = 3;
+
+// ------------------------------------------------------------------ urid:map
+struct UridTable {
+    std::mutex mu;
+    std::map<std::string, LV2_URID> ids;
+    std::vector<std::string> uris;
+    LV2_URID map(const char* uri)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = ids.find(uri);
+        if (it != ids.end()) return it->second;
+        uris.push_back(uri);
+        const LV2_URID id = (LV2_URID)uris.size();
+        ids[uri] = id;
+        return id;
+    }
+};
+LV2_URID urid_map_cb(LV2_URID_Map_Handle h, const char* uri) { return ((UridTable*)h)->map(uri); }
+
+// ------------------------------------------------------------------ log:log
+int log_vprintf_cb(LV2_Log_Handle h, LV2_URID, const char* fmt, va_list ap)
+{
+    if (!*(bool*)h) return 0;
+    return vfprintf(stderr, fmt, ap);
+}
+int log_printf_cb(LV2_Log_Handle h, LV2_URID type, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    const int r = log_vprintf_cb(h, type, fmt, ap);
+    va_end(ap);
+    return r;
+}
+
+// ------------------------------------------------------------------ state:mapPath (identity)
+char* map_abstract(LV2_State_Map_Path_Handle, const char* p) { return strdup(p); }
+char* map_absolute(LV2_State_Map_Path_Handle, const char* p) { return strdup(p); }
+
+// ------------------------------------------------------------------ a tiny thread pool
+class Pool {
+public:
+    explicit Pool(int n) : n_(std::max(1, n))
+    {
+        for (int i = 1; i < n_; ++i) threads_.emplace_back([this, i] { loop(i); });
+    }
+    ~Pool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            ++gen_;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    int size() const { return n_; }
+    // runs fn(worker_index) on every worker (the caller is worker 0) and waits
+    void run(const std::function<void(int)>& fn)
+    {
+        if (n_ == 1) { fn(0); return; }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn;
+            pending_ = n_ - 1;
+            ++gen_;
+        }
+        cv_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [this] { return pending_ == 0; });
+    }
+
+private:
+    void loop(int idx)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)>* fn;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                fn = fn_;
+            }
+            (*fn)(idx);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) done_cv_.notify_one();
+            }
+        }
+    }
+    int n_;
+    std::vector<std::thread> threads_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
+struct Instance;
+struct WorkItem { std::vector<uint8_t> data; };
+
+struct Instance {
+    LV2_Handle handle = nullptr;
+    aidax_host* host = nullptr;
+    LV2_Worker_Schedule schedule{};
+    LV2_Feature f_map{}, f_sched{}, f_log{};
+    const LV2_Feature* features[4] = {};
+    std::deque<WorkItem> scheduled;  // written by run()/work_response (audio context)
+    std::deque<WorkItem> responses;  // written by work() through respond()
+    std::vector<uint8_t> control_buf; // only while a patch:Set is pending
+    bool control_pending = false;
+    uint8_t* notify_buf = nullptr;
+    int notify_count = 0;
+    std::string last_notify_path;
+};
+
+} // namespace
+
+struct aidax_host {
+    void* dl = nullptr;
+    const LV2_Descriptor* desc = nullptr;
+    const LV2_Worker_Interface* worker = nullptr;
+    const LV2_State_Interface* state = nullptr;
+    const AidaxBatchInterface* batch = nullptr;
+    double sample_rate = 48000.0;
+    int n = 0, max_block = 0;
+    size_t stride = 0;
+    float* in = nullptr;
+    float* out = nullptr;
+    bool arena_from_plugin = false;
+    std::vector<float> controls; // [n][kPortCount]
+    std::vector<Instance> inst;
+    std::vector<uint8_t> notify_storage;
+    uint32_t notify_cap = 0;
+    alignas(8) uint8_t empty_seq[sizeof(LV2_Atom_Sequence)];
+    UridTable urids;
+    LV2_URID_Map map{};
+    LV2_Log_Log log{};
+    bool verbose = false;
+    LV2_URID u_sequence = 0, u_object = 0, u_urid = 0, u_path = 0, u_patch_set = 0, u_patch_property = 0, u_patch_value = 0, u_json = 0;
+    std::unique_ptr<Pool> pool;
+    std::atomic<bool> any_scheduled{false};
+};
+
+namespace {
+
+LV2_Worker_Status schedule_cb(LV2_Worker_Schedule_Handle h, uint32_t size, const void* data)
+{
+    Instance* in = (Instance*)h;
+    WorkItem w;
+    w.data.assign((const uint8_t*)data, (const uint8_t*)data + size);
+    in->scheduled.push_back(std::move(w));
+    in->host->any_scheduled.store(true, std::memory_order_relaxed);
+    return LV2_WORKER_SUCCESS;
+}
+LV2_Worker_Status respond_cb(LV2_Worker_Respond_Handle h, uint32_t size, const void* data)
+{
+    Instance* in = (Instance*)h;
+    WorkItem w;
+    w.data.assign((const uint8_t*)data, (const uint8_t*)data + size);
+    in->responses.push_back(std::move(w));
+    return LV2_WORKER_SUCCESS;
+}
+
+void init_sequence(uint8_t* buf, uint32_t body_size, LV2_URID seq_type)
+{
+    LV2_Atom_Sequence* s = (LV2_Atom_Sequence*)buf;
+    s->atom.size = body_size;
+    s->atom.type = seq_type;
+    s->body.unit = 0;
+    s->body.pad = 0;
+}
+
+// forge a sequence holding one patch:Set{property=#json, value=Path}
+void build_load_message(aidax_host* h, Instance& in, const char* path)
+{
+    const uint32_t cap = 256 + (uint32_t)strlen(path);
+    in.control_buf.assign(cap, 0);
+    LV2_Atom_Forge forge;
+    lv2_atom_forge_init(&forge, &h->map);
+    lv2_atom_forge_set_buffer(&forge, in.control_buf.data(), cap);
+    LV2_Atom_Forge_Frame seq_frame, obj_frame;
+    lv2_atom_forge_sequence_head(&forge, &seq_frame, 0);
+    lv2_atom_forge_frame_time(&forge, 0);
+    lv2_atom_forge_object(&forge, &obj_frame, 0, h->u_patch_set);
+    lv2_atom_forge_key(&forge, h->u_patch_property);
+    lv2_atom_forge_urid(&forge, h->u_json);
+    lv2_atom_forge_key(&forge, h->u_patch_value);
+    lv2_atom_forge_path(&forge, path, (uint32_t)strlen(path));
+    lv2_atom_forge_pop(&forge, &obj_frame);
+    lv2_atom_forge_pop(&forge, &seq_frame);
+    in.control_pending = true;
+}
+
+// count patch:Set notifications in an instance's NOTIFY buffer
+void scan_notify(aidax_host* h, Instance& in)
+{
+    const LV2_Atom_Sequence* seq = (const LV2_Atom_Sequence*)in.notify_buf;
+    if (seq->atom.type != h->u_sequence || seq->atom.size > h->notify_cap) return; // untouched (still "capacity")
+    LV2_ATOM_SEQUENCE_FOREACH(seq, ev)
+    {
+        if (ev->body.type != h->u_object) continue;
+        const LV2_Atom_Object* obj = (const LV2_Atom_Object*)&ev->body;
+        if (obj->body.otype != h->u_patch_set) continue;
+        const LV2_Atom* value = nullptr;
+        lv2_atom_object_get(obj, h->u_patch_value, &value, 0);
+        in.notify_count++;
+        if (value && value->type == h->u_path) in.last_notify_path = (const char*)(value + 1);
+    }
+}
+
+void run_instances(aidax_host* h, int lo, int hi, uint32_t n_samples)
+{
+    for (int i = lo; i < hi; ++i) {
+        Instance& in = h->inst[i];
+        // an LV2 host presents an output atom port as an empty chunk whose size is the capacity
+        LV2_Atom_Sequence* ns = (LV2_Atom_Sequence*)in.notify_buf;
+        ns->atom.size = h->notify_cap - (uint32_t)sizeof(LV2_Atom);
+        ns->atom.type = 0;
+        if (in.control_pending) h->desc->connect_port(in.handle, kPortControl, in.control_buf.data());
+        h->desc->run(in.handle, n_samples);
+        if (in.control_pending) {
+            h->desc->connect_port(in.handle, kPortControl, h->empty_seq);
+            in.control_pending = false;
+            in.control_buf.clear();
+        }
+    }
+}
+
+// The worker round trip of one instance: work() for everything scheduled, then work_response()
+// for every reply (which may schedule follow-up work, e.g. freeing the previous model).
+void drain_worker(aidax_host* h, Instance& in)
+{
+    for (int round = 0; round < 4 && (!in.scheduled.empty() || !in.responses.empty()); ++round) {
+        while (!in.scheduled.empty()) {
+            WorkItem w = std::move(in.scheduled.front());
+            in.scheduled.pop_front();
+            if (h->worker && h->worker->work) h->worker->work(in.handle, respond_cb, &in, (uint32_t)w.data.size(), w.data.data());
+        }
+        while (!in.responses.empty()) {
+            WorkItem w = std::move(in.responses.front());
+            in.responses.pop_front();
+            if (h->worker && h->worker->work_response) h->worker->work_response(in.handle, (uint32_t)w.data.size(), w.data.data());
+        }
+    }
+}
+
+struct StateStore { std::string value; LV2_URID key = 0; };
+LV2_State_Status store_cb(LV2_State_Handle hd, uint32_t key, const void* value, size_t size, uint32_t, uint32_t)
+{
+    StateStore* s = (StateStore*)hd;
+    s->key = key;
+    s->value.assign((const char*)value, size ? size - 1 : 0);
+    return LV2_STATE_SUCCESS;
+}
+const void* retrieve_cb(LV2_State_Handle hd, uint32_t key, size_t* size, uint32_t* type, uint32_t* flags)
+{
+    StateStore* s = (StateStore*)hd;
+    if (key != s->key) return nullptr;
+    *size = s->value.size() + 1;
+    *type = 0;
+    *flags = LV2_STATE_IS_POD | LV2_STATE_IS_PORTABLE;
+    return s->value.c_str();
+}
+
+} // namespace
+
+extern "C" {
+
+const char* aidax_host_error(void) { return g_err.c_str(); }
+
+aidax_host* aidax_host_open(const char* plugin_so, double sample_rate, int n_instances, int max_block, int n_threads, int device)
+{
+    if (!plugin_so || n_instances <= 0 || max_block <= 0) { set_err("bad arguments"); return nullptr; }
+    std::unique_ptr<aidax_host> h(new aidax_host());
+    h->dl = dlopen(plugin_so, RTLD_NOW | RTLD_LOCAL);
+    if (!h->dl) { set_err("dlopen(%s): %s", plugin_so, dlerror()); return nullptr; }
+    auto fn = (LV2_Descriptor_Function)dlsym(h->dl, "lv2_descriptor");
+    if (!fn) { set_err("%s does not export lv2_descriptor", plugin_so); return nullptr; }
+    h->desc = fn(0);
+    if (!h->desc) { set_err("lv2_descriptor(0) returned NULL"); return nullptr; }
+    h->worker = (const LV2_Worker_Interface*)h->desc->extension_data(LV2_WORKER__interface);
+    h->state = (const LV2_State_Interface*)h->desc->extension_data(LV2_STATE__interface);
+    h->batch = (const AidaxBatchInterface*)h->desc->extension_data(AIDAX_BATCH__interface);
+    if (h->batch && h->batch->abi_version != AIDAX_BATCH_ABI_VERSION) h->batch = nullptr;
+    // AIDAX_HOST_NO_BATCH=1: behave like a stock LV2 host (every run() renders on its own)
+    const bool no_batch = getenv("AIDAX_HOST_NO_BATCH") != nullptr;
+    const AidaxBatchInterface* batch_for_setup = h->batch;
+    h->sample_rate = sample_rate;
+    h->n = n_instances;
+    h->max_block = max_block;
+    h->stride = (size_t)((max_block + 31) & ~31);
+    h->verbose = getenv("AIDAX_HOST_VERBOSE") != nullptr;
+    h->map.handle = &h->urids;
+    h->map.map = urid_map_cb;
+    h->log.handle = &h->verbose;
+    h->log.printf = log_printf_cb;
+    h->log.vprintf = log_vprintf_cb;
+    h->u_sequence = h->urids.map(LV2_ATOM__Sequence);
+    h->u_object = h->urids.map(LV2_ATOM__Object);
+    h->u_urid = h->urids.map(LV2_ATOM__URID);
+    h->u_path = h->urids.map(LV2_ATOM__Path);
+    h->u_patch_set = h->urids.map(LV2_PATCH__Set);
+    h->u_patch_property = h->urids.map(LV2_PATCH__property);
+    h->u_patch_value = h->urids.map(LV2_PATCH__value);
+    h->u_json = h->urids.map((std::string(h->desc->URI) + "#json").c_str());
+    init_sequence(h->empty_seq, sizeof(LV2_Atom_Sequence_Body), h->u_sequence);
+
+    const size_t arena_bytes = (size_t)n_instances * h->stride * sizeof(float);
+    if (batch_for_setup && batch_for_setup->configure(n_instances, max_block, device) != 0) {
+        set_err("plugin engine already sized differently");
+        return nullptr;
+    }
+    if (no_batch) h->batch = nullptr;
+    if (h->batch) {
+        h->in = (float*)h->batch->arena_alloc(arena_bytes);
+        h->out = (float*)h->batch->arena_alloc(arena_bytes);
+        h->arena_from_plugin = true;
+        if (!h->in || !h->out) { set_err("pinned arena allocation failed: %s", h->batch->last_error()); return nullptr; }
+    } else {
+        h->in = (float*)aligned_alloc(64, arena_bytes);
+        h->out = (float*)aligned_alloc(64, arena_bytes);
+        if (!h->in || !h->out) { set_err("arena allocation failed"); return nullptr; }
+    }
+    memset(h->in, 0, arena_bytes);
+    memset(h->out, 0, arena_bytes);
+
+    // ttl defaults (ttl/rt-neural-generic.ttl:92-313)
+    h->controls.assign((size_t)n_instances * kPortCount, 0.f);
+    for (int i = 0; i < n_instances; ++i) {
+        float* c = &h->controls[(size_t)i * kPortCount];
+        c[4] = 66.216f; c[12] = 305.f; c[14] = 750.f; c[15] = 0.707f; c[18] = 2000.f; c[21] = 1.f; c[24] = 1.f;
+    }
+    h->notify_cap = n_instances <= 8192 ? 2048u : 384u;
+    h->notify_storage.assign((size_t)n_instances * h->notify_cap, 0);
+    h->inst.resize(n_instances);
+    for (int i = 0; i < n_instances; ++i) {
+        Instance& in = h->inst[i];
+        in.host = h.get();
+        in.schedule.handle = &in;
+        in.schedule.schedule_work = schedule_cb;
+        in.f_map = LV2_Feature{LV2_URID__map, &h->map};
+        in.f_sched = LV2_Feature{LV2_WORKER__schedule, &in.schedule};
+        in.f_log = LV2_Feature{LV2_LOG__log, &h->log};
+        in.features[0] = &in.f_map; in.features[1] = &in.f_sched; in.features[2] = &in.f_log; in.features[3] = nullptr;
+        in.notify_buf = h->notify_storage.data() + (size_t)i * h->notify_cap;
+        in.handle = h->desc->instantiate(h->desc, sample_rate, "", in.features);
+        if (!in.handle) {
+            set_err("instantiate failed for instance %d", i);
+            for (int k = 0; k < i; ++k) h->desc->cleanup(h->inst[k].handle);
+            return nullptr;
+        }
+        h->desc->connect_port(in.handle, kPortIn, h->in + (size_t)i * h->stride);
+        h->desc->connect_port(in.handle, kPortOut, h->out + (size_t)i * h->stride);
+        h->desc->connect_port(in.handle, kPortControl, h->empty_seq);
+        h->desc->connect_port(in.handle, kPortNotify, in.notify_buf);
+        for (int p = 4; p < kPortCount; ++p) h->desc->connect_port(in.handle, p, &h->controls[(size_t)i * kPortCount + p]);
+    }
+    h->pool.reset(new Pool(n_threads));
+    return h.release();
+}
+
+void aidax_host_close(aidax_host* h)
+{
+    if (!h) return;
+    h->pool.reset();
+    for (Instance& in : h->inst)
+        if (in.handle) {
+            drain_worker(h, in);
+            h->desc->cleanup(in.handle);
+        }
+    if (h->arena_from_plugin) { h->batch->arena_free(h->in); h->batch->arena_free(h->out); }
+    else { free(h->in); free(h->out); }
+    // the plugin binary stays loaded: it may own process-wide state (CUDA context, engine)
+    delete h;
+}
+
+int aidax_host_n_instances(const aidax_host* h) { return h ? h->n : 0; }
+int aidax_host_is_batched(const aidax_host* h) { return h && h->batch ? 1 : 0; }
+uint64_t aidax_host_launch_count(const aidax_host* h) { return h && h->batch ? h->batch->launch_count() : 0; }
+float* aidax_host_input(aidax_host* h) { return h ? h->in : nullptr; }
+float* aidax_host_output(aidax_host* h) { return h ? h->out : nullptr; }
+size_t aidax_host_stride(const aidax_host* h) { return h ? h->stride : 0; }
+
+int aidax_host_set_control(aidax_host* h, int instance, int port, float value)
+{
+    if (!h || port < 4 || port >= kPortCount || instance >= h->n) { set_err("bad control address"); return 1; }
+    if (instance >= 0) h->controls[(size_t)instance * kPortCount + port] = value;
+    else for (int i = 0; i < h->n; ++i) h->controls[(size_t)i * kPortCount + port] = value;
+    return 0;
+}
+
+float aidax_host_get_control(const aidax_host* h, int instance, int port)
+{
+    if (!h || port < 4 || port >= kPortCount || instance < 0 || instance >= h->n) return 0.f;
+    return h->controls[(size_t)instance * kPortCount + port];
+}
+
+int aidax_host_load_model(aidax_host* h, int instance, const char* json_path)
+{
+    if (!h || !json_path || instance >= h->n) { set_err("bad arguments"); return 1; }
+    if (instance >= 0) build_load_message(h, h->inst[instance], json_path);
+    else for (Instance& in : h->inst) build_load_message(h, in, json_path);
+    return 0;
+}
+
+int aidax_host_activate(aidax_host* h)
+{
+    if (!h) return 1;
+    if (h->desc->activate) for (Instance& in : h->inst) h->desc->activate(in.handle);
+    return 0;
+}
+int aidax_host_deactivate(aidax_host* h)
+{
+    if (!h) return 1;
+    if (h->desc->deactivate) for (Instance& in : h->inst) h->desc->deactivate(in.handle);
+    return 0;
+}
+
+int aidax_host_run(aidax_host* h, int n_samples)
+{
+    if (!h || n_samples < 0 || n_samples > h->max_block) { set_err("bad n_samples"); return 1; }
+    const int nt = h->pool->size();
+    const int n = h->n;
+    int rc = 0;
+    if (h->batch) h->batch->begin();
+    h->pool->run([&](int w) {
+        const int lo = (int)((int64_t)n * w / nt), hi = (int)((int64_t)n * (w + 1) / nt);
+        run_instances(h, lo, hi, (uint32_t)n_samples);
+    });
+    if (h->batch) {
+        rc = h->batch->end();
+        if (rc) set_err("batch end failed: %s", h->batch->last_error());
+    }
+    if (h->any_scheduled.load(std::memory_order_relaxed)) {
+        h->any_scheduled.store(false, std::memory_order_relaxed);
+        h->pool->run([&](int w) {
+            const int lo = (int)((int64_t)n * w / nt), hi = (int)((int64_t)n * (w + 1) / nt);
+            for (int i = lo; i < hi; ++i) {
+                Instance& in = h->inst[i];
+                if (in.scheduled.empty() && in.responses.empty()) continue;
+                drain_worker(h, in);
+                scan_notify(h, in);
+            }
+        });
+    }
+    return rc;
+}
+
+int aidax_host_notify_count(const aidax_host* h, int instance)
+{
+    return (h && instance >= 0 && instance < h->n) ? h->inst[instance].notify_count : 0;
+}
+const char* aidax_host_last_notify_path(const aidax_host* h, int instance)
+{
+    return (h && instance >= 0 && instance < h->n) ? h->inst[instance].last_notify_path.c_str() : "";
+}
+
+int aidax_host_save_state(aidax_host* h, int instance, char* path_out, int path_cap)
+{
+    if (!h || !h->state || instance < 0 || instance >= h->n) { set_err("no state interface"); return -1; }
+    LV2_State_Map_Path mp{nullptr, map_abstract, map_absolute};
+    LV2_Feature f_mp{LV2_STATE__mapPath, &mp};
+    const LV2_Feature* feats[] = {&f_mp, nullptr};
+    StateStore st;
+    const int rc = (int)h->state->save(h->inst[instance].handle, store_cb, &st, 0, feats);
+    if (path_out && path_cap > 0) snprintf(path_out, (size_t)path_cap, "%s", st.value.c_str());
+    return rc;
+}
+
+int aidax_host_restore_state(aidax_host* h, int instance, const char* path)
+{
+    if (!h || !h->state || !path || instance < 0 || instance >= h->n) { set_err("no state interface"); return -1; }
+    LV2_State_Map_Path mp{nullptr, map_abstract, map_absolute};
+    LV2_Feature f_mp{LV2_STATE__mapPath, &mp};
+    const LV2_Feature* feats[] = {&f_mp, nullptr};
+    StateStore st;
+    st.key = h->u_json;
+    st.value = path;
+    const int rc = (int)h->state->restore(h->inst[instance].handle, retrieve_cb, &st, 0, feats);
+    h->any_scheduled.store(true, std::memory_order_relaxed); // restore schedules a load; run it with the next period
+    return rc;
+}
+
+} // extern "C"

@@ -498,6 +498,45 @@ int aidax_model_describe(aidax_engine* e, int model_id, aidax_model_desc* out)
     return AIDAX_OK;
 }
 
+int aidax_model_check_json(const char* path, aidax_model_desc* out)
+{
+    if (!path) return fail(AIDAX_ERR_ARG, "null path");
+    try {
+        const HostModel hm = load_model_file(path);
+        (void)pack_model(hm);
+        if (out) *out = hm.desc;
+    } catch (const std::exception& ex) {
+        return fail(AIDAX_ERR_MODEL, "Unable to load json file: %s Error: %s", path, ex.what());
+    }
+    return AIDAX_OK;
+}
+
+int aidax_design_biquad(int type, double fc, double q, double gain_db, double coef[5])
+{
+    if (!coef || type < 0 || type > 6) return fail(AIDAX_ERR_ARG, "bad biquad arguments");
+    const BiquadCoef c = design_biquad(type, fc, q, gain_db);
+    coef[0] = c.a0; coef[1] = c.a1; coef[2] = c.a2; coef[3] = c.b1; coef[4] = c.b2;
+    return AIDAX_OK;
+}
+
+int aidax_decode_controls(double sample_rate, const float controls[AIDAX_N_CONTROLS], int loading, int model_bound,
+                          uint32_t* flags, float* pre_target, float* master_target, double coefs[35])
+{
+    if (!controls) return fail(AIDAX_ERR_ARG, "null controls");
+    StreamHost sh;
+    init_stream_host(sh, sample_rate);
+    decode_controls(sh, controls, loading != 0, model_bound != 0);
+    if (flags) *flags = sh.flags;
+    if (pre_target) *pre_target = sh.pre_target;
+    if (master_target) *master_target = sh.master_target;
+    if (coefs)
+        for (int b = 0; b < kNumBiquads; ++b) {
+            const BiquadCoef& c = sh.bq[b];
+            coefs[b * 5 + 0] = c.a0; coefs[b * 5 + 1] = c.a1; coefs[b * 5 + 2] = c.a2; coefs[b * 5 + 3] = c.b1; coefs[b * 5 + 4] = c.b2;
+        }
+    return AIDAX_OK;
+}
+
 int aidax_stream_open(aidax_engine* e, double sample_rate, int* stream_id_out)
 {
     if (!e || !stream_id_out) return fail(AIDAX_ERR_ARG, "null argument");
@@ -612,6 +651,17 @@ int aidax_streams_set_params(aidax_engine* e, int first_stream, int n, const flo
         e->dirty_ctrl[s] = 1;
     }
     e->any_dirty = true;
+    return AIDAX_OK;
+}
+
+int aidax_stream_get_params(aidax_engine* e, int stream, float* target1, float* target2)
+{
+    int rc = check_stream(e, stream);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    const StreamHost& sh = e->streams[stream];
+    if (target1) *target1 = sh.model >= 0 ? sh.param_target[0] : 0.f;
+    if (target2) *target2 = sh.model >= 0 ? sh.param_target[1] : 0.f;
     return AIDAX_OK;
 }
 

@@ -1,0 +1,493 @@
+// plugin.cpp -- rt-neural-generic.so: the reference's LV2 surface on top of the CUDA engine.
+//
+// Same URI, same 25-port table, same worker/state extension data, same patch:Set model loading
+// and notify message as AidaDSP/aidadsp-lv2 rt-neural-generic (rt-neural-generic.cpp:11-29,
+// 244-333, 376-480, 484-660, 681-893; uris.h:26-94; ttl/rt-neural-generic.ttl) -- but an instance
+// holds no DSP: it is a handle on one stream of a process-wide aidax engine, and run() either
+// renders that single stream synchronously (plain LV2 hosts) or, inside a batch opened through the
+// #batch extension (include/aidax_batch.h), defers to one launch for all instances.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/aidax.h"
+#include "../../include/aidax_batch.h"
+#include "../../include/aidax_lv2_abi.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------- port table
+// ports_t, rt-neural-generic.h:84-112 (AIDADSP_MODEL_LOADER=1, AIDADSP_PARAMS=2, optional dc blocker)
+enum Port : uint32_t {
+    P_IN = 0, P_OUT_1, P_CONTROL, P_NOTIFY, P_IN_LPF, P_PREGAIN, P_NET_BYPASS, P_PARAM1, P_PARAM2, P_EQ_BYPASS, P_EQ_POS,
+    P_BASS, P_BFREQ, P_MID, P_MFREQ, P_MIDQ, P_MTYPE, P_TREBLE, P_TFREQ, P_DEPTH, P_PRESENCE, P_DCBLOCKER, P_MASTER,
+    P_INPUT_SIZE, P_ENABLED, P_COUNT
+};
+static_assert((int)P_IN_LPF == (int)AIDAX_CTRL_PORT_BASE && (int)P_COUNT == (int)AIDAX_CTRL_PORT_BASE + (int)AIDAX_N_CONTROLS, "port table drifted");
+
+#define PLUGIN__json AIDAX_PLUGIN_URI "#json"
+#define PLUGIN__applyJson AIDAX_PLUGIN_URI "#applyJson"
+
+struct Uris { // uris.h:33-67
+    LV2_URID atom_Float, atom_Path, atom_Resource, atom_Sequence, atom_URID, atom_eventTransfer, applyJson, json,
+        midi_Event, param_gain, patch_Get, patch_Set, patch_property, patch_value;
+};
+
+// worker messages, rt-neural-generic.h:132-157
+enum WorkerMessageType { kWorkerLoad, kWorkerApply, kWorkerFree };
+struct WorkerMessage { WorkerMessageType type; };
+struct WorkerLoadMessage { WorkerMessageType type; char path[1024]; };
+struct LoadedModel { int model_id; int input_size; char* path; float old_param1, old_param2; };
+struct WorkerApplyMessage { WorkerMessageType type; LoadedModel* model; };
+
+// ---------------------------------------------------------------------------- process-wide engine
+struct EngineHub {
+    std::mutex mu;
+    aidax_engine* engine = nullptr;
+    int max_instances = 0, max_block = 0, device = -1;
+    int refs = 0;
+    // batch state
+    bool batching = false;
+    struct Pending { int stream; const float* in; float* out; uint32_t n; };
+    std::vector<Pending> pending;
+    float* stage_in = nullptr;  // pinned staging rows for scattered port buffers
+    float* stage_out = nullptr;
+};
+EngineHub g_hub;
+
+int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+// Creates the engine on first use.  Sizes: configure() > environment > defaults.
+aidax_engine* hub_engine()
+{
+    std::lock_guard<std::mutex> lk(g_hub.mu);
+    if (g_hub.engine) return g_hub.engine;
+    if (g_hub.max_instances <= 0) g_hub.max_instances = env_int("AIDAX_MAX_STREAMS", 1024);
+    if (g_hub.max_block <= 0) g_hub.max_block = env_int("AIDAX_MAX_BLOCK", 2048);
+    if (g_hub.device < 0) g_hub.device = env_int("AIDAX_DEVICE", 0);
+    if (aidax_engine_create(g_hub.device, g_hub.max_instances, g_hub.max_block, &g_hub.engine) != AIDAX_OK) {
+        fprintf(stderr, "rt-neural-generic (aidax): cannot create the CUDA engine: %s\n", aidax_last_error());
+        g_hub.engine = nullptr;
+    }
+    return g_hub.engine;
+}
+
+int batch_configure(int max_instances, int max_block, int device)
+{
+    std::lock_guard<std::mutex> lk(g_hub.mu);
+    if (g_hub.engine)
+        return (max_instances <= g_hub.max_instances && max_block <= g_hub.max_block && (device < 0 || device == g_hub.device)) ? 0 : AIDAX_ERR_STATE;
+    g_hub.max_instances = max_instances;
+    g_hub.max_block = max_block;
+    if (device >= 0) g_hub.device = device;
+    return 0;
+}
+
+int batch_begin()
+{
+    std::lock_guard<std::mutex> lk(g_hub.mu);
+    g_hub.batching = true;
+    g_hub.pending.clear();
+    return 0;
+}
+
+// Renders a set of deferred run() calls with as few engine calls as possible: runs of consecutive
+// stream ids whose port buffers are rows of one arena (constant stride) go straight from the
+// caller's memory; anything else is gathered through pinned staging rows.
+int render_pending(std::vector<EngineHub::Pending>& items)
+{
+    aidax_engine* e = g_hub.engine;
+    if (!e || items.empty()) return 0;
+    std::sort(items.begin(), items.end(), [](const EngineHub::Pending& a, const EngineHub::Pending& b) { return a.stream < b.stream; });
+    size_t i = 0;
+    while (i < items.size()) {
+        const EngineHub::Pending& a = items[i];
+        size_t j = i + 1;
+        ptrdiff_t stride = 0;
+        bool regular = true;
+        if (j < items.size() && items[j].stream == a.stream + 1 && items[j].n == a.n) {
+            stride = items[j].in - a.in;
+            regular = stride >= (ptrdiff_t)a.n && (items[j].out - a.out) == stride;
+            if (regular)
+                while (j < items.size() && items[j].stream == a.stream + (int)(j - i) && items[j].n == a.n &&
+                       items[j].in == a.in + (ptrdiff_t)(j - i) * stride && items[j].out == a.out + (ptrdiff_t)(j - i) * stride)
+                    ++j;
+            else
+                j = i + 1;
+        }
+        const int count = (int)(j - i);
+        int rc;
+        if (count > 1) {
+            rc = aidax_render_host(e, a.stream, count, (int)a.n, a.in, a.out, AIDAX_LAYOUT_PLANAR, (size_t)stride);
+        } else {
+            rc = aidax_render_host(e, a.stream, 1, (int)a.n, a.in, a.out, AIDAX_LAYOUT_PLANAR, a.n);
+        }
+        if (rc) return rc;
+        i = j;
+    }
+    return 0;
+}
+
+int batch_end()
+{
+    std::vector<EngineHub::Pending> items;
+    {
+        std::lock_guard<std::mutex> lk(g_hub.mu);
+        g_hub.batching = false;
+        items.swap(g_hub.pending);
+    }
+    return render_pending(items);
+}
+
+uint64_t batch_launch_count() { return g_hub.engine ? aidax_engine_launch_count(g_hub.engine) : 0; }
+
+const AidaxBatchInterface g_batch_iface = {
+    AIDAX_BATCH_ABI_VERSION, batch_configure, aidax_host_alloc, aidax_host_free, batch_begin, batch_end, batch_launch_count, aidax_last_error,
+};
+
+// ---------------------------------------------------------------------------- one plugin instance
+struct Plugin {
+    // ports
+    const float* in = nullptr;
+    float* out_1 = nullptr;
+    const LV2_Atom_Sequence* control_port = nullptr;
+    LV2_Atom_Sequence* notify_port = nullptr;
+    float* ctl[P_COUNT] = {};
+    // host features
+    LV2_URID_Map* map = nullptr;
+    LV2_Worker_Schedule* schedule = nullptr;
+    LV2_Log_Log* log = nullptr;
+    LV2_Log_Logger logger{};
+    LV2_Atom_Forge forge{};
+    LV2_Atom_Forge_Frame notify_frame{};
+    Uris uris{};
+    // state
+    double samplerate = 48000.0;
+    aidax_engine* engine = nullptr;
+    int stream = -1;
+    bool loading = true;      // rt-neural-generic.cpp:318
+    int last_input_size = 0;  // :316
+    LoadedModel* model = nullptr;
+    float latched[AIDAX_N_CONTROLS];
+    bool latched_valid = false;
+    bool latched_loading = true;
+};
+
+void map_uris(LV2_URID_Map* map, Uris* u)
+{
+    u->atom_Float = map->map(map->handle, LV2_ATOM__Float);
+    u->atom_Path = map->map(map->handle, LV2_ATOM__Path);
+    u->atom_Resource = map->map(map->handle, LV2_ATOM__Resource);
+    u->atom_Sequence = map->map(map->handle, LV2_ATOM__Sequence);
+    u->atom_URID = map->map(map->handle, LV2_ATOM__URID);
+    u->atom_eventTransfer = map->map(map->handle, LV2_ATOM__eventTransfer);
+    u->applyJson = map->map(map->handle, PLUGIN__applyJson);
+    u->json = map->map(map->handle, PLUGIN__json);
+    u->midi_Event = map->map(map->handle, LV2_MIDI__MidiEvent);
+    u->param_gain = map->map(map->handle, LV2_PARAMETERS__gain);
+    u->patch_Get = map->map(map->handle, LV2_PATCH__Get);
+    u->patch_Set = map->map(map->handle, LV2_PATCH__Set);
+    u->patch_property = map->map(map->handle, LV2_PATCH__property);
+    u->patch_value = map->map(map->handle, LV2_PATCH__value);
+}
+
+void free_loaded(LoadedModel* m)
+{
+    if (!m) return;
+    free(m->path);
+    delete m;
+}
+
+// ---------------------------------------------------------------------------- LV2 callbacks
+
+// rt-neural-generic.cpp:244-333
+LV2_Handle instantiate(const LV2_Descriptor*, double samplerate, const char*, const LV2_Feature* const* features)
+{
+    Plugin* self = new Plugin();
+    self->samplerate = samplerate;
+    for (int i = 0; features && features[i]; ++i) {
+        if (!strcmp(features[i]->URI, LV2_URID__map)) self->map = (LV2_URID_Map*)features[i]->data;
+        else if (!strcmp(features[i]->URI, LV2_WORKER__schedule)) self->schedule = (LV2_Worker_Schedule*)features[i]->data;
+        else if (!strcmp(features[i]->URI, LV2_LOG__log)) self->log = (LV2_Log_Log*)features[i]->data;
+    }
+    if (!self->map) {
+        fprintf(stderr, "Error! Missing feature urid:map %s %d\n", __func__, __LINE__);
+        delete self;
+        return nullptr;
+    }
+    if (!self->schedule) {
+        fprintf(stderr, "Error! Missing feature work:schedule %s %d\n", __func__, __LINE__);
+        delete self;
+        return nullptr;
+    }
+    map_uris(self->map, &self->uris);
+    lv2_log_logger_init(&self->logger, self->map, self->log);
+    lv2_atom_forge_init(&self->forge, self->map);
+
+    self->engine = hub_engine();
+    if (!self->engine || aidax_stream_open(self->engine, samplerate, &self->stream) != AIDAX_OK) {
+        // No CPU fallback: without the CUDA engine the plugin cannot exist.
+        lv2_log_error(&self->logger, "aidax engine unavailable: %s\n", aidax_last_error());
+        delete self;
+        return nullptr;
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_hub.mu);
+        g_hub.refs++;
+    }
+    self->loading = true;
+    self->last_input_size = 0;
+    self->model = nullptr;
+    return (LV2_Handle)self;
+}
+
+// rt-neural-generic.cpp:376-480
+void connect_port(LV2_Handle instance, uint32_t port, void* data)
+{
+    Plugin* self = (Plugin*)instance;
+    switch (port) {
+    case P_IN: self->in = (const float*)data; break;
+    case P_OUT_1: self->out_1 = (float*)data; break;
+    case P_CONTROL: self->control_port = (const LV2_Atom_Sequence*)data; break;
+    case P_NOTIFY: self->notify_port = (LV2_Atom_Sequence*)data; break;
+    default:
+        if (port < P_COUNT) self->ctl[port] = (float*)data;
+        break;
+    }
+}
+
+// rt-neural-generic.cpp:337-365
+void activate(LV2_Handle instance)
+{
+    Plugin* self = (Plugin*)instance;
+    aidax_stream_activate(self->engine, self->stream);
+}
+
+void deactivate(LV2_Handle) {}
+
+// rt-neural-generic.cpp:484-660
+void run(LV2_Handle instance, uint32_t n_samples)
+{
+    Plugin* self = (Plugin*)instance;
+    const Uris* uris = &self->uris;
+
+    // control ports -> engine (only when something changed; the decode itself mirrors :489-517)
+    float c[AIDAX_N_CONTROLS];
+    for (int i = 0; i < AIDAX_N_CONTROLS; ++i) {
+        const float* p = self->ctl[AIDAX_CTRL_PORT_BASE + i];
+        c[i] = (p && i != AIDAX_CTRL_MODELINSIZE) ? *p : 0.f;
+    }
+    if (self->ctl[P_INPUT_SIZE]) *self->ctl[P_INPUT_SIZE] = (float)self->last_input_size; // :518
+
+    // atom messages (:526-586)
+    if (self->notify_port && self->control_port) {
+        const uint32_t notify_capacity = self->notify_port->atom.size;
+        lv2_atom_forge_set_buffer(&self->forge, (uint8_t*)self->notify_port, notify_capacity);
+        lv2_atom_forge_sequence_head(&self->forge, &self->notify_frame, 0);
+        LV2_ATOM_SEQUENCE_FOREACH(self->control_port, ev)
+        {
+            if (!lv2_atom_forge_is_object_type(&self->forge, ev->body.type)) {
+                lv2_log_trace(&self->logger, "Unknown event type %d\n", ev->body.type);
+                continue;
+            }
+            const LV2_Atom_Object* obj = (const LV2_Atom_Object*)&ev->body;
+            if (obj->body.otype != uris->patch_Set) {
+                lv2_log_trace(&self->logger, "Unknown object type %d\n", obj->body.otype);
+                continue;
+            }
+            const LV2_Atom* property = nullptr;
+            const LV2_Atom* value = nullptr;
+            lv2_atom_object_get(obj, uris->patch_property, &property, uris->patch_value, &value, 0);
+            if (!property) { lv2_log_trace(&self->logger, "patch:Set message with no property\n"); continue; }
+            if (property->type != uris->atom_URID) { lv2_log_trace(&self->logger, "patch:Set property is not a URID\n"); continue; }
+            if (((const LV2_Atom_URID*)property)->body != uris->json) { lv2_log_trace(&self->logger, "patch:Set property body is not json\n"); continue; }
+            if (!value) { lv2_log_trace(&self->logger, "patch:Set message with no value\n"); continue; }
+            if (value->type != uris->atom_Path) { lv2_log_trace(&self->logger, "patch:Set value is not a Path\n"); continue; }
+            lv2_log_trace(&self->logger, "Queueing set message\n");
+            WorkerLoadMessage msg;
+            memset(&msg, 0, sizeof(msg));
+            msg.type = kWorkerLoad;
+            memcpy(msg.path, value + 1, std::min(value->size, (uint32_t)(sizeof(msg.path) - 1u)));
+            self->schedule->schedule_work(self->schedule->handle, sizeof(msg), &msg);
+            self->loading = true;
+        }
+    }
+
+    if (!self->latched_valid || self->latched_loading != self->loading || memcmp(c, self->latched, sizeof(c)) != 0) {
+        aidax_stream_set_controls(self->engine, self->stream, c, self->loading ? 1 : 0);
+        memcpy(self->latched, c, sizeof(c));
+        self->latched_valid = true;
+        self->latched_loading = self->loading;
+    }
+
+    if (n_samples == 0) return; // pre-run (:606-609)
+    if (!self->in || !self->out_1) return;
+
+    bool deferred = false;
+    {
+        std::lock_guard<std::mutex> lk(g_hub.mu);
+        if (g_hub.batching) {
+            g_hub.pending.push_back(EngineHub::Pending{self->stream, self->in, self->out_1, n_samples});
+            deferred = true;
+        }
+    }
+    if (!deferred) {
+        // lone instance: render this stream now and wait, so run() has LV2 semantics
+        const int rc = aidax_render_host(self->engine, self->stream, 1, (int)n_samples, self->in, self->out_1, AIDAX_LAYOUT_PLANAR, n_samples);
+        if (rc != AIDAX_OK) {
+            lv2_log_error(&self->logger, "aidax render failed: %s\n", aidax_last_error());
+            if (self->out_1 != self->in) memcpy(self->out_1, self->in, sizeof(float) * n_samples);
+        }
+    }
+}
+
+// rt-neural-generic.cpp:664-677
+void cleanup(LV2_Handle instance)
+{
+    Plugin* self = (Plugin*)instance;
+    aidax_stream_close(self->engine, self->stream);
+    free_loaded(self->model);
+    {
+        std::lock_guard<std::mutex> lk(g_hub.mu);
+        g_hub.refs--;
+    }
+    delete self;
+}
+
+// rt-neural-generic.cpp:707-759
+LV2_State_Status restore(LV2_Handle instance, LV2_State_Retrieve_Function retrieve, LV2_State_Handle handle, uint32_t,
+                         const LV2_Feature* const* features)
+{
+    Plugin* self = (Plugin*)instance;
+    size_t size = 0;
+    uint32_t type = 0, valflags = 0;
+    const void* value = retrieve(handle, self->uris.json, &size, &type, &valflags);
+    if (value) {
+        lv2_log_note(&self->logger, "Restoring file %s\n", (const char*)value);
+        WorkerLoadMessage msg;
+        memset(&msg, 0, sizeof(msg));
+        msg.type = kWorkerLoad;
+        LV2_State_Map_Path* map_path = nullptr;
+        LV2_State_Free_Path* free_path = nullptr;
+        for (int i = 0; features && features[i]; ++i) {
+            if (!strcmp(features[i]->URI, LV2_STATE__mapPath)) map_path = (LV2_State_Map_Path*)features[i]->data;
+            else if (!strcmp(features[i]->URI, LV2_STATE__freePath)) free_path = (LV2_State_Free_Path*)features[i]->data;
+        }
+        if (map_path) {
+            char* apath = map_path->absolute_path(map_path->handle, (const char*)value);
+            memcpy(msg.path, apath, std::min(strlen(apath), sizeof(msg.path) - 1u));
+            if (free_path) free_path->free_path(free_path->handle, apath);
+            else free(apath);
+        } else {
+            memcpy(msg.path, value, std::min(size, sizeof(msg.path) - 1u));
+        }
+        self->schedule->schedule_work(self->schedule->handle, sizeof(msg), &msg);
+    }
+    return LV2_STATE_SUCCESS;
+}
+
+// rt-neural-generic.cpp:763-796
+LV2_State_Status save(LV2_Handle instance, LV2_State_Store_Function store, LV2_State_Handle handle, uint32_t,
+                      const LV2_Feature* const* features)
+{
+    Plugin* self = (Plugin*)instance;
+    if (!self->model) return LV2_STATE_SUCCESS; // nothing loaded yet
+    LV2_State_Map_Path* map_path = nullptr;
+    for (int i = 0; features && features[i]; ++i)
+        if (!strcmp(features[i]->URI, LV2_STATE__mapPath)) map_path = (LV2_State_Map_Path*)features[i]->data;
+    if (!map_path) return LV2_STATE_ERR_NO_FEATURE;
+    char* apath = map_path->abstract_path(map_path->handle, self->model->path);
+    store(handle, self->uris.json, apath, strlen(apath) + 1, self->uris.atom_Path, LV2_STATE_IS_POD | LV2_STATE_IS_PORTABLE);
+    free(apath);
+    return LV2_STATE_SUCCESS;
+}
+
+// rt-neural-generic.cpp:807-848 (+ loadModelFromPath :963-1085: parse, variant selection, weights -> engine)
+LV2_Worker_Status work(LV2_Handle instance, LV2_Worker_Respond_Function respond, LV2_Worker_Respond_Handle handle, uint32_t,
+                       const void* data)
+{
+    Plugin* self = (Plugin*)instance;
+    const WorkerMessage* msg = (const WorkerMessage*)data;
+    switch (msg->type) {
+    case kWorkerLoad: {
+        const char* path = ((const WorkerLoadMessage*)data)->path;
+        float p1 = 0.f, p2 = 0.f;
+        aidax_stream_get_params(self->engine, self->stream, &p1, &p2); // :822-825
+        int model_id = -1, input_size = 0;
+        if (aidax_model_load_json(self->engine, path, &model_id, &input_size) == AIDAX_OK) {
+            lv2_log_note(&self->logger, "Successfully loaded json file: %s\n", path);
+            LoadedModel* m = new LoadedModel{model_id, input_size, strdup(path), p1, p2};
+            // "cache input size for later" (:1082): published before the swap, as in the reference
+            self->last_input_size = input_size;
+            WorkerApplyMessage reply = {kWorkerApply, m};
+            respond(handle, sizeof(reply), &reply);
+        } else {
+            // failed load: old model keeps running, `loading` stays set and the output stays muted (:1017-1020, 1041-1044)
+            lv2_log_error(&self->logger, "%s\n", aidax_last_error());
+        }
+        return LV2_WORKER_SUCCESS;
+    }
+    case kWorkerFree:
+        free_loaded(((const WorkerApplyMessage*)data)->model);
+        return LV2_WORKER_SUCCESS;
+    case kWorkerApply:
+        break; // should not happen
+    }
+    return LV2_WORKER_ERR_UNKNOWN;
+}
+
+// rt-neural-generic.cpp:859-893
+LV2_Worker_Status work_response(LV2_Handle instance, uint32_t, const void* data)
+{
+    Plugin* self = (Plugin*)instance;
+    const WorkerMessage* msg = (const WorkerMessage*)data;
+    if (msg->type != kWorkerApply) return LV2_WORKER_ERR_UNKNOWN;
+
+    WorkerApplyMessage reply = {kWorkerFree, self->model};
+    self->model = ((const WorkerApplyMessage*)data)->model;
+    // swap: bind the new model; the engine resets and pre-warms the recurrent state on the GPU
+    aidax_stream_set_model(self->engine, self->stream, self->model->model_id, self->model->old_param1, self->model->old_param2);
+    self->schedule->schedule_work(self->schedule->handle, sizeof(reply), &reply);
+    lv2_log_trace(&self->logger, "New model in use\n");
+
+    // report the change to host/ui (write_set_file, uris.h:76-94)
+    if (self->forge.buf) {
+        lv2_atom_forge_frame_time(&self->forge, 0);
+        LV2_Atom_Forge_Frame frame;
+        lv2_atom_forge_object(&self->forge, &frame, 0, self->uris.patch_Set);
+        lv2_atom_forge_key(&self->forge, self->uris.patch_property);
+        lv2_atom_forge_urid(&self->forge, self->uris.json);
+        lv2_atom_forge_key(&self->forge, self->uris.patch_value);
+        lv2_atom_forge_path(&self->forge, self->model->path, (uint32_t)strlen(self->model->path) + 1);
+        lv2_atom_forge_pop(&self->forge, &frame);
+    }
+    self->loading = false;
+    lv2_log_trace(&self->logger, "loading = false\n");
+    return LV2_WORKER_SUCCESS;
+}
+
+// rt-neural-generic.cpp:681-698
+const void* extension_data(const char* uri)
+{
+    static const LV2_State_Interface state = {save, restore};
+    static const LV2_Worker_Interface worker = {work, work_response, nullptr};
+    if (!strcmp(uri, LV2_STATE__interface)) return &state;
+    if (!strcmp(uri, LV2_WORKER__interface)) return &worker;
+    if (!strcmp(uri, AIDAX_BATCH__interface)) return &g_batch_iface;
+    return nullptr;
+}
+
+const LV2_Descriptor g_descriptor = {AIDAX_PLUGIN_URI, instantiate, connect_port, activate, run, deactivate, cleanup, extension_data};
+
+} // namespace
+
+// rt-neural-generic.cpp:24-29
+LV2_SYMBOL_EXPORT const LV2_Descriptor* lv2_descriptor(uint32_t index) { return index == 0 ? &g_descriptor : nullptr; }

@@ -224,3 +224,38 @@ class Engine:
 
     def synchronize(self):
         self._chk(self.lib.aidax_engine_synchronize(self.h))
+
+
+# ---- host-only helpers (no GPU needed)
+def check_json(path):
+    lib = load_library()
+    lib.aidax_model_check_json.argtypes = [C.c_char_p, C.POINTER(ModelDesc)]
+    d = ModelDesc()
+    rc = lib.aidax_model_check_json(os.fsencode(path), C.byref(d))
+    if rc != 0:
+        raise AidaxError(rc, lib.aidax_last_error().decode())
+    return d
+
+
+def design_biquad(type_, fc, q, gain_db):
+    lib = load_library()
+    lib.aidax_design_biquad.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double)]
+    out = np.zeros(5, dtype=np.float64)
+    rc = lib.aidax_design_biquad(type_, fc, q, gain_db, out.ctypes.data_as(C.POINTER(C.c_double)))
+    if rc != 0:
+        raise AidaxError(rc, lib.aidax_last_error().decode())
+    return out
+
+
+def decode_controls(controls, samplerate=48000.0, loading=False, model_bound=True):
+    lib = load_library()
+    lib.aidax_decode_controls.argtypes = [C.c_double, C.POINTER(C.c_float), C.c_int, C.c_int, C.POINTER(C.c_uint32),
+                                          C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_double)]
+    c = np.ascontiguousarray(controls, dtype=np.float32)
+    flags, pre, master = C.c_uint32(0), C.c_float(0), C.c_float(0)
+    coefs = np.zeros(35, dtype=np.float64)
+    rc = lib.aidax_decode_controls(samplerate, _fptr(c), int(loading), int(model_bound), C.byref(flags), C.byref(pre), C.byref(master),
+                                   coefs.ctypes.data_as(C.POINTER(C.c_double)))
+    if rc != 0:
+        raise AidaxError(rc, lib.aidax_last_error().decode())
+    return flags.value, pre.value, master.value, coefs.reshape(7, 5)

@@ -132,6 +132,20 @@ int aidax_model_load_json(aidax_engine* e, const char* path, int* model_id_out, 
 
 int aidax_model_describe(aidax_engine* e, int model_id, aidax_model_desc* out);
 
+/* Host-only (no GPU needed): parse + validate a model file with the rules above and report what
+ * would be registered.  AIDAX_OK or AIDAX_ERR_MODEL (aidax_last_error() has the reason). */
+int aidax_model_check_json(const char* path, aidax_model_desc* out);
+
+/* Host-only: the control-rate arithmetic, exposed for verification against the reference.
+ * aidax_design_biquad: Biquad::calcBiquad (common/Biquad.cpp:67-165), type 0..6 = lowpass, highpass,
+ *   bandpass, notch, peak, lowshelf, highshelf; fc normalised; coef = {a0,a1,a2,b1,b2}.
+ * aidax_decode_controls: what one run() derives from its control ports for a fresh instance
+ *   (rt-neural-generic.cpp:489-517, 50-127): flag word (layout.h F_*), gain targets and the 7x5 filter
+ *   coefficients in the order in_lpf, depth, bass, mid, treble, presence, dc. */
+int aidax_design_biquad(int type, double fc, double q, double gain_db, double coef[5]);
+int aidax_decode_controls(double sample_rate, const float controls[AIDAX_N_CONTROLS], int loading, int model_bound,
+                          uint32_t* flags, float* pre_target, float* master_target, double coefs[35]);
+
 /* ----------------------------------------------------------------- streams ---- */
 
 /* Open a stream: mirrors RtNeuralGeneric::instantiate (rt-neural-generic.cpp:244-333):
@@ -157,6 +171,10 @@ int aidax_stream_set_controls(aidax_engine* e, int stream, const float controls[
 /* Bulk variant of set_controls for PARAM1/PARAM2 automation: p1/p2 are [n] arrays for streams
  * first..first+n-1 (stream ids are dense small integers in open order). */
 int aidax_streams_set_params(aidax_engine* e, int first_stream, int n, const float* p1, const float* p2);
+
+/* Current targets of the PARAM1/PARAM2 smoothers of the bound model (0,0 if none): what the reference
+ * reads with param1Coeff.getTargetValue() in work() (rt-neural-generic.cpp:822-825) to seed the next model. */
+int aidax_stream_get_params(aidax_engine* e, int stream, float* target1, float* target2);
 
 /* Test/debug observability: copy the recurrent state (h[hidden], c[hidden]; c only for LSTM) and
  * the 7x2 biquad states (order: in_lpf, depth, bass, mid, treble, presence, dc) of a stream. */
