@@ -354,6 +354,23 @@ static int check_stream(aidax_engine* e, int s)
 
 } // namespace aidax
 
+// ------------------------------------------------------------------ FP32 pipe peak probe
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters)
+{
+    float a[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = 1.0f + 1e-3f * (float)(threadIdx.x + j);
+    const float x = 0.9999f, y = 1e-4f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = fmaf(a[j], x, y);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += a[j];
+    if (s == 123.456f) out[0] = s; // never true; keeps the loop alive
+}
+
 // ================================================================================ C ABI
 extern "C" {
 
@@ -775,6 +792,39 @@ void* aidax_host_alloc(size_t bytes)
     return p;
 }
 void aidax_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int aidax_measure_fp32_peak(int device, int millis, double* tflops_out)
+{
+    if (!tflops_out) return fail(AIDAX_ERR_ARG, "null output");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    float* d = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d, sizeof(float)));
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a));
+    CUDA_TRY(cudaEventCreate(&b));
+    const int grid = prop.multiProcessorCount * 8, iters = 8192;
+    const double flop_per_launch = (double)grid * 256.0 * 16.0 * 2.0 * iters;
+    fp32_peak_kernel<<<grid, 256>>>(d, iters); // warm-up
+    CUDA_TRY(cudaDeviceSynchronize());
+    double best = 0.0, spent = 0.0;
+    while (spent < (double)millis) {
+        CUDA_TRY(cudaEventRecord(a));
+        fp32_peak_kernel<<<grid, 256>>>(d, iters);
+        CUDA_TRY(cudaEventRecord(b));
+        CUDA_TRY(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+        spent += ms;
+        best = std::max(best, flop_per_launch / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    *tflops_out = best;
+    return AIDAX_OK;
+}
 
 uint64_t aidax_engine_launch_count(aidax_engine* e) { return e ? e->launches : 0; }
 

@@ -226,6 +226,17 @@ class Engine:
         self._chk(self.lib.aidax_engine_synchronize(self.h))
 
 
+def measure_fp32_peak(device=0, millis=200):
+    """Sustained FFMA throughput of the device in TFLOP/s (roofline denominator of the recurrence kernels)."""
+    lib = load_library()
+    lib.aidax_measure_fp32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
+    v = C.c_double(0.0)
+    rc = lib.aidax_measure_fp32_peak(device, millis, C.byref(v))
+    if rc != 0:
+        raise AidaxError(rc, lib.aidax_last_error().decode())
+    return v.value
+
+
 # ---- host-only helpers (no GPU needed)
 def check_json(path):
     lib = load_library()

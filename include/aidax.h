@@ -206,6 +206,10 @@ int aidax_engine_synchronize(aidax_engine* e);
 void* aidax_host_alloc(size_t bytes);
 void aidax_host_free(void* p);
 
+/* Roofline denominator for the recurrence kernels: sustained FP32 FFMA throughput (TFLOP/s, 2 flop per
+ * FFMA) of `device`, measured with a register-resident FFMA loop over all SMs for about `millis` ms. */
+int aidax_measure_fp32_peak(int device, int millis, double* tflops_out);
+
 /* Number of kernel launches issued by the engine since creation (for bench accounting). */
 uint64_t aidax_engine_launch_count(aidax_engine* e);
 

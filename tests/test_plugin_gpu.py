@@ -1,0 +1,200 @@
+"""GPU: the CUDA-backed LV2 plugin through the batch-render host vs the UNMODIFIED reference plugin through
+the same host, same control values, same patch:Set messages, same audio (tier A)."""
+import os
+
+import numpy as np
+import pytest
+
+import aidadsp_lv2_b200 as ax
+from aidadsp_lv2_b200 import models, signals
+from oracle import pyref
+from conftest import bundled_model_paths
+
+pytestmark = pytest.mark.gpu
+T = 128
+REF_PLUGIN = os.path.join(pyref.REF_DIR, "rt-neural-generic.so")
+N_INST = 8
+
+
+def _cases():
+    return [
+        ax.default_controls(),
+        ax.default_controls(EQPOS=1.0, BASS=3.0, MID=-2.0, TREBLE=4.0, DEPTH=1.0, PRESENCE=2.0, PREGAIN=6.0, MASTER=-3.0),
+        ax.default_controls(EQPOS=0.0, BASS=-8.0, MID=8.0, MIDQ=2.5, TREBLE=-4.0, DEPTH=-1.0, PRESENCE=-2.0, ANTIALIASING=0.0),
+        ax.default_controls(MTYPE=1.0, MID=5.0, MFREQ=1200.0, DCBLOCKER=0.0, ANTIALIASING=100.0),
+        ax.default_controls(EQBYPASS=1.0, PREGAIN=-12.0, MASTER=15.0, NETBYPASS=1.0),
+        ax.default_controls(ENABLED=0.0),
+        ax.default_controls(EQPOS=1.0, MID=3.0, PARAM1=0.25, PARAM2=0.75),
+        ax.default_controls(EQBYPASS=1.0),
+    ]
+
+
+def _open_pair(n_threads=1):
+    if not os.path.exists(REF_PLUGIN):
+        pytest.skip("oracle/_ref not built")
+    ours = ax.BatchHost(ax.plugin_path(), n_instances=N_INST, max_block=T, n_threads=n_threads)
+    ref = ax.BatchHost(REF_PLUGIN, n_instances=N_INST, max_block=T)
+    cases = _cases()
+    for h in (ours, ref):
+        for i, c in enumerate(cases):
+            for port in range(4, 25):
+                if port != 23:
+                    h.set_control(port, c[port - 4], instance=i)
+    return ours, ref, cases
+
+
+def test_plugin_matches_reference_with_model_swaps(native_libs, tmp_path):
+    ours, ref, cases = _open_pair()
+    assert ours.batched and not ref.batched
+    paths = bundled_model_paths()
+    # NB: an UNconditioned model.  For input_size 2/3 the reference's xsimd path multiplies an unspecified
+    # 4th stack lane into the gates (ModelT.h:263-264 + kernel_mat_mul, SURVEY.md hazard H1), so its own
+    # output depends on stack residue; conditioned models are checked against the scalar truth instead
+    # (test_conditioned_hot_swap_vs_oracle below, tests/test_oracle.py tier C).
+    gru = str(tmp_path / "gru_16_1.json")
+    models.save_json(models.synthetic(models.CELL_GRU, 16, 1, seed=4242, in_skip=1, in_gain_db=-2.0, out_gain_db=1.5), gru)
+    bad = str(tmp_path / "bad.json")
+    open(bad, "w").write("{\"in_shape\": [null, null, 9]}")
+    NB = 90
+    x = signals.sweep_noise_block(N_INST, T * NB)
+    yo, yr = np.empty_like(x), np.empty_like(x)
+    for b in range(NB):
+        if b == 0:
+            for h in (ours, ref):
+                h.load_model(paths[0])
+        if b == 25:       # hot swap LSTM-12 -> GRU-16 (skip connection, in/out gains) on every instance
+            for h in (ours, ref):
+                h.load_model(gru)
+        if b == 40:       # PARAM ports move (no audible effect for input_size 1, but the smoothers track them)
+            for h in (ours, ref):
+                h.set_control("PARAM1", 0.9)
+                h.set_control("PARAM2", 0.1)
+        if b == 55:       # failed load: old model keeps running, output fades to silence, ModelInSize unchanged
+            for h in (ours, ref):
+                h.load_model(bad, instance=1)
+        if b == 70:       # recovery with another bundled model
+            for h in (ours, ref):
+                h.load_model(paths[3], instance=1)
+        sl = slice(b * T, (b + 1) * T)
+        yo[:, sl] = ours.process(x[:, sl])
+        yr[:, sl] = ref.process(x[:, sl])
+        for i in (0, 1):
+            assert ours.get_control("MODELINSIZE", i) == ref.get_control("MODELINSIZE", i), (b, i)
+            assert ours.notify_count(i) == ref.notify_count(i), (b, i)
+    assert ours.last_notify_path(1) == ref.last_notify_path(1) == paths[3]
+    assert ours.last_notify_path(0) == gru
+    err = np.abs(yo - yr).max(axis=1)
+    assert err.max() <= 1e-4, err
+    assert np.abs(yr[1, 69 * T:70 * T]).max() < 1e-3 and np.abs(yo[1, 69 * T:70 * T]).max() < 1e-3  # muted by the failed load
+    assert np.array_equal(yo[4], yr[4])   # network bypassed: bit exact
+    assert np.array_equal(yo[5], x[5])    # disabled: straight copy
+    assert ours.save_state(0) == ref.save_state(0)
+    assert ours.launch_count > 0
+    ours.close()
+    ref.close()
+
+
+def test_lone_instance_run_equals_batched(native_libs, monkeypatch):
+    """A host that ignores the #batch extension (stock LV2 host): every run() renders synchronously on its own."""
+    ours, ref, cases = _open_pair()
+    path = bundled_model_paths()[1]
+    NB = 20
+    x = signals.sweep_noise_block(N_INST, T * NB)
+    ours.load_model(path)
+    yb = np.concatenate([ours.process(x[:, b * T:(b + 1) * T]) for b in range(NB)], axis=1)
+    ours.close()
+    ref.close()
+    monkeypatch.setenv("AIDAX_HOST_NO_BATCH", "1")
+    lone = ax.BatchHost(ax.plugin_path(), n_instances=N_INST, max_block=T)
+    assert not lone.batched
+    for i, c in enumerate(cases):
+        for port in range(4, 25):
+            if port != 23:
+                lone.set_control(port, c[port - 4], instance=i)
+    lone.load_model(path)
+    yl = np.concatenate([lone.process(x[:, b * T:(b + 1) * T]) for b in range(NB)], axis=1)
+    assert np.abs(yl - yb).max() <= 2e-6
+    lone.close()
+
+
+def test_ten_seconds_north_star_tolerance(native_libs):
+    """C1 on the GPU path: the six bundled models, EQ on (post, every band non-trivial), 10 s sweep+noise in 128-sample
+    buffers vs the reference binary: max abs <= 1e-4 and SNR >= 90 dB, drift tracked per 1 s window."""
+    if not os.path.exists(REF_PLUGIN):
+        pytest.skip("oracle/_ref not built")
+    paths = bundled_model_paths()
+    n = len(paths)
+    ours = ax.BatchHost(ax.plugin_path(), n_instances=N_INST, max_block=T)
+    ref = ax.BatchHost(REF_PLUGIN, n_instances=n, max_block=T, n_threads=min(n, os.cpu_count() or 1))
+    for h in (ours, ref):
+        for k, v in dict(EQPOS=0.0, BASS=3.0, MID=-2.0, TREBLE=4.0, DEPTH=1.0, PRESENCE=2.0).items():
+            h.set_control(k, v)
+        for i, p in enumerate(paths):
+            h.load_model(p, instance=i)
+    NB = 3750
+    x = np.zeros((N_INST, T * NB), dtype=np.float32)
+    x[:n] = signals.sweep_noise_block(n, T * NB)
+    yo = np.empty((n, T * NB), dtype=np.float32)
+    yr = np.empty_like(yo)
+    for b in range(NB):
+        sl = slice(b * T, (b + 1) * T)
+        yo[:, sl] = ours.process(x[:, sl])[:n]
+        yr[:, sl] = ref.process(x[:n, sl])
+    err = np.abs(yo - yr)
+    assert err.max() <= 1e-4, err.max(axis=1)
+    snr = 10 * np.log10((yr.astype(np.float64) ** 2).sum(axis=1) / np.maximum((err.astype(np.float64) ** 2).sum(axis=1), 1e-300))
+    assert snr.min() >= 90.0, snr
+    per_second = err.reshape(n, 10, -1).max(axis=2)
+    assert per_second[:, -1].max() <= 4 * max(per_second[:, 1].max(), 2e-6)  # no drift growth first -> last second
+    ours.close()
+    ref.close()
+
+
+def test_conditioned_hot_swap_vs_oracle(native_libs, tmp_path):
+    """Conditioned models (input_size 2 -> 3) through the plugin surface: model swap hands the old PARAM targets to
+    the new model's smoothers (work(), rt-neural-generic.cpp:822-825), 2048-sample pre-warm with parked params,
+    first-run snap, 0.1 s linear ramps on automation.  Truth = the oracle (scalar W.x), see H1 note above."""
+    from oracle import pyoracle
+    n = N_INST
+    ours = ax.BatchHost(ax.plugin_path(), n_instances=n, max_block=T)
+    m2 = models.synthetic(models.CELL_LSTM, 20, 2, seed=31, in_gain_db=1.0)
+    m3 = models.synthetic(models.CELL_GRU, 16, 3, seed=32, in_skip=1, out_gain_db=-1.0)
+    p2, p3 = str(tmp_path / "m2.json"), str(tmp_path / "m3.json")
+    models.save_json(m2, p2)
+    models.save_json(m3, p3)
+    ctl = [ax.default_controls(PARAM1=0.1 * i, PARAM2=1.0 - 0.1 * i, EQPOS=float(i % 2)) for i in range(n)]
+    for i, c in enumerate(ctl):
+        for port in range(4, 25):
+            if port != 23:
+                ours.set_control(port, c[port - 4], instance=i)
+    orcs = [pyoracle.OracleStream() for _ in range(n)]
+    NB = 120
+    x = signals.sweep_noise_block(n, T * NB)
+    worst = 0.0
+    for b in range(NB):
+        if b == 0:
+            ours.load_model(p2)
+        if b == 30:
+            ours.load_model(p3)
+        if b in (50, 80):  # automation: new targets, linear ramps over 4800 samples
+            for i in range(n):
+                ctl[i][ax.CTRL["PARAM1"]] = (0.37 * (i + 1) + 0.01 * b) % 1.0
+                ctl[i][ax.CTRL["PARAM2"]] = (0.61 * (i + 2) + 0.02 * b) % 1.0
+                ours.set_control("PARAM1", ctl[i][ax.CTRL["PARAM1"]], instance=i)
+                ours.set_control("PARAM2", ctl[i][ax.CTRL["PARAM2"]], instance=i)
+        sl = slice(b * T, (b + 1) * T)
+        for o in orcs:
+            if b in (0, 30):
+                o.set_loading(True)   # patch:Set seen in this run() -> master target 0 for this period
+        y = ours.process(x[:, sl])
+        yo = np.stack([o.run(ctl[i], x[i, sl]) for i, o in enumerate(orcs)])
+        worst = max(worst, float(np.abs(y - yo).max()))
+        if b == 0:
+            for o in orcs:
+                o.set_model(m2)
+        if b == 30:
+            for o in orcs:
+                o.set_model(m3)
+    assert ours.get_control("MODELINSIZE") == 3.0
+    assert worst <= 1e-4, worst
+    ours.close()
