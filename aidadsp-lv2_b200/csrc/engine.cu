@@ -62,7 +62,8 @@ struct ModelEntry {
 
 struct Family {       // one kernel family = (cell, hidden); cell 2 = streams without a network
     int cell, H;
-    std::vector<const KernelVariant*> variants; // sorted by S ascending
+    std::vector<const KernelVariant*> variants; // FP32 variants, sorted by streams per warp ascending
+    const KernelVariant* tc = nullptr;          // tensor-core variant (kind 1), if compiled for this hidden size
 };
 
 struct LaunchPlan {
@@ -84,14 +85,19 @@ struct aidax_engine {
     cudaStream_t stream = nullptr;
     std::mutex mu;
     int tile_mode = 0, math_mode = 0;
+    int tc_min_streams = 4096; // auto mode: families at least this large run on the tensor-core variant
     int sm_count = 148;
-    size_t smem_optin = 0;
+    size_t smem_optin = 0, smem_per_sm = 0;
     uint64_t launches = 0;
 
     // host shadows
     std::vector<StreamHost> streams;
     int n_open_hi = 0; // one past the highest stream id ever opened
     std::vector<uint8_t> dirty_ctrl, dirty_coef, dirty_cmd;
+    // streams whose PARAM1/2 port value differs from the smoother target the reference would hold: the only
+    // ones the per-render host bookkeeping has to visit (keeps a render call O(changed streams), not O(streams))
+    std::vector<int> track_list;
+    std::vector<uint8_t> track_flag;
     std::vector<uint32_t> h_flags, h_cmd;
     std::vector<float> h_pre_target, h_master_target, h_p_port, h_p_init, h_cmd_pre_mem, h_cmd_master_mem, h_exp_coef, h_lin_denom;
     std::vector<double> h_bq_coef;
@@ -148,13 +154,24 @@ static void collect_families(aidax_engine* e)
             for (Family& f : e->families)
                 if (f.cell == kv->cell && (kv->cell == 2 || f.H == kv->H)) fam = &f;
             if (!fam) { e->families.push_back(Family{kv->cell, kv->H, {}}); fam = &e->families.back(); }
-            fam->variants.push_back(kv);
+            if (kv->kind == 1) fam->tc = kv;
+            else fam->variants.push_back(kv);
         }
     for (Family& f : e->families)
         std::stable_sort(f.variants.begin(), f.variants.end(), [](const KernelVariant* a, const KernelVariant* b) { return a->ws < b->ws; });
 }
 
 static void mark_ctrl(aidax_engine* e, int s) { e->dirty_ctrl[s] = 1; e->any_dirty = true; }
+
+static void note_param_tracking(aidax_engine* e, int s)
+{
+    const StreamHost& sh = e->streams[s];
+    if (e->track_flag[s]) return;
+    if (float_not_equal(sh.param_target[0], sh.ctrl[AIDAX_CTRL_PARAM1]) || float_not_equal(sh.param_target[1], sh.ctrl[AIDAX_CTRL_PARAM2])) {
+        e->track_flag[s] = 1;
+        e->track_list.push_back(s);
+    }
+}
 
 static void write_coefs(aidax_engine* e, int s, uint32_t mask)
 {
@@ -178,6 +195,7 @@ static void sync_stream_shadow(aidax_engine* e, int s)
     e->h_p_port[s] = sh.ctrl[AIDAX_CTRL_PARAM1];
     e->h_p_port[(size_t)e->cap + s] = sh.ctrl[AIDAX_CTRL_PARAM2];
     mark_ctrl(e, s);
+    note_param_tracking(e, s);
 }
 
 // upload [lo, hi) of a per-stream array with `rows` rows of pitch cap
@@ -243,6 +261,7 @@ static int upload_dirty(aidax_engine* e, int first, int n)
 static const KernelVariant* choose_variant(const aidax_engine* e, const Family& fam, int n_streams)
 {
     const auto& v = fam.variants;
+    if (fam.tc && (e->tile_mode == 3 || (e->tile_mode == 0 && n_streams >= e->tc_min_streams))) return fam.tc;
     if (v.size() == 1) return v[0];
     if (e->tile_mode == 1) return v.front();
     if (e->tile_mode == 2) return v.back();
@@ -318,11 +337,10 @@ static int launch_all(aidax_engine* e, int first, int n, int n_samples, const fl
     if (rc) return rc;
     for (const LaunchPlan& lp : e->plan) {
         const KernelVariant* kv = lp.kv;
-        const int weights_floats = kv->cell == 2 ? 0 : packed_weight_floats(kv->H);
-        // samples per shared-memory sub-block: as many as fit with >= 2 CTAs per SM, capped at the period
+        // samples per shared-memory sub-block: as many as fit with the variant's target residency, capped at the period
         int ts = n_samples;
-        const size_t budget = e->smem_optin / 2 - 1024;
-        auto smem_for = [&](int t) { return (size_t)(weights_floats + kv->NW * kv->warp_smem_floats(t, lp.max_param_tiles)) * sizeof(float); };
+        const size_t budget = std::min(e->smem_optin, e->smem_per_sm / (size_t)kv->ctas_per_sm - 1024);
+        auto smem_for = [&](int t) { return (size_t)(kv->fixed_smem_floats + kv->NW * kv->warp_smem_floats(t, lp.max_param_tiles)) * sizeof(float); };
         while (ts > 8 && smem_for(ts) > budget) ts = (ts + 1) / 2;
         if (smem_for(ts) > e->smem_optin) return fail(AIDAX_ERR_CAPACITY, "kernel variant needs %zu B shared memory", smem_for(ts));
         const size_t smem = smem_for(ts);
@@ -395,10 +413,13 @@ int aidax_engine_create(int device, int max_streams, int max_block, aidax_engine
     e->max_block = max_block;
     e->sm_count = prop.multiProcessorCount;
     e->smem_optin = prop.sharedMemPerBlockOptin;
+    e->smem_per_sm = prop.sharedMemPerMultiprocessor;
+    if (const char* v = std::getenv("AIDAX_TC_MIN_STREAMS")) e->tc_min_streams = std::atoi(v);
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     const size_t cap = (size_t)e->cap;
     e->streams.resize(cap);
     e->dirty_ctrl.assign(cap, 0); e->dirty_coef.assign(cap, 0); e->dirty_cmd.assign(cap, 0);
+    e->track_flag.assign(cap, 0);
     e->h_flags.assign(cap, 0); e->h_cmd.assign(cap, 0);
     e->h_pre_target.assign(cap, 0.f); e->h_master_target.assign(cap, 0.f);
     e->h_p_port.assign(2 * cap, 0.f); e->h_p_init.assign(2 * cap, 0.f);
@@ -441,7 +462,7 @@ void* aidax_engine_cuda_stream(aidax_engine* e) { return e ? (void*)e->stream : 
 
 int aidax_engine_configure(aidax_engine* e, int tile_mode, int math_mode)
 {
-    if (!e || tile_mode < 0 || tile_mode > 2 || math_mode < 0 || math_mode > 1) return fail(AIDAX_ERR_ARG, "bad configure arguments");
+    if (!e || tile_mode < 0 || tile_mode > 3 || math_mode < 0 || math_mode > 1) return fail(AIDAX_ERR_ARG, "bad configure arguments");
     std::lock_guard<std::mutex> lk(e->mu);
     e->tile_mode = tile_mode;
     e->math_mode = math_mode;
@@ -666,6 +687,7 @@ int aidax_streams_set_params(aidax_engine* e, int first_stream, int n, const flo
         if (p1) { sh.ctrl[AIDAX_CTRL_PARAM1] = p1[i]; e->h_p_port[s] = p1[i]; }
         if (p2) { sh.ctrl[AIDAX_CTRL_PARAM2] = p2[i]; e->h_p_port[(size_t)e->cap + s] = p2[i]; }
         e->dirty_ctrl[s] = 1;
+        note_param_tracking(e, s);
     }
     e->any_dirty = true;
     return AIDAX_OK;
@@ -733,8 +755,14 @@ static int render_common_checks(aidax_engine* e, int first, int n, int n_samples
 static void after_render(aidax_engine* e, int first, int n, int n_samples)
 {
     const int last = std::min(first + n, e->n_open_hi);
-    for (int s = first; s < last; ++s)
+    size_t keep = 0;
+    for (size_t i = 0; i < e->track_list.size(); ++i) {
+        const int s = e->track_list[i];
+        if (s < first || s >= last) { e->track_list[keep++] = s; continue; }
         if (e->streams[s].open) track_param_targets(e->streams[s], n_samples);
+        e->track_flag[s] = 0; // any later change of the ports, flags or model re-lists the stream
+    }
+    e->track_list.resize(keep);
 }
 
 int aidax_render_device(aidax_engine* e, int first_stream, int n_streams, int n_samples, const float* d_in, float* d_out,

@@ -3,6 +3,7 @@
 // the low-latency shape (one stream per group, many lanes), the last the throughput shape
 // (register tile of S streams x 4U gate rows per lane, >= 10 FFMA per 128-bit shared load).
 #include "kernels.cuh"
+#include "kernels_tc.cuh"
 #include "variants.h"
 
 #ifndef AIDAX_VARIANT_H
@@ -17,8 +18,17 @@ static int wsf(int ts, int np) { return Tile<0, H, L, S>::warp_smem_floats(ts, n
 #define V(CELL, Hh, Ll, Ss, NWw)                                                                         \
     { CELL, Hh, Ll, Ss, NWw, (32 / Ll) * Ss,                                                             \
       { (const void*)&chain_kernel<CELL, Hh, Ll, Ss, NWw, 0>, (const void*)&chain_kernel<CELL, Hh, Ll, Ss, NWw, 1> }, \
-      &wsf<Hh, Ll, Ss> }
+      &wsf<Hh, Ll, Ss>, 0, CELL == 2 ? 0 : (Hh + 3) * Hh * 4 + Hh * 4 + Hh + 4, 2 }
 #define BOTH(Hh, Ll, Ss, NWw) V(0, Hh, Ll, Ss, NWw), V(1, Hh, Ll, Ss, NWw)
+
+// tensor-core variants: NT tiles of 128 streams per CTA, RES CTAs per SM
+template <int H>
+static int wsf_tc(int ts, int np) { return TcShape<H>::warp_floats(ts, np); }
+#define VT(CELL, Hh, NTt, RES)                                                                           \
+    { CELL, Hh, 0, 0, NTt * 4, 32,                                                                       \
+      { (const void*)&chain_kernel_tc<CELL, Hh, NTt, RES, 0>, (const void*)&chain_kernel_tc<CELL, Hh, NTt, RES, 1> }, \
+      &wsf_tc<Hh>, 1, (TcShape<Hh>::fixed_floats(NTt) + 3) & ~3, RES }
+#define BOTH_TC(Hh, NTt, RES) VT(0, Hh, NTt, RES), VT(1, Hh, NTt, RES)
 
 #define CAT_(a, b) a##b
 #define CAT(a, b) CAT_(a, b)
@@ -27,19 +37,19 @@ const KernelVariant CAT(kVariantsH, AIDAX_VARIANT_H)[] = {
 #if AIDAX_VARIANT_H == 0
     V(2, 8, 8, 8, 4),
 #elif AIDAX_VARIANT_H == 8
-    BOTH(8, 8, 1, 4), BOTH(8, 8, 4, 4), BOTH(8, 8, 8, 4),
+    BOTH(8, 8, 1, 4), BOTH(8, 8, 4, 4), BOTH(8, 8, 8, 4), BOTH_TC(8, 1, 4),
 #elif AIDAX_VARIANT_H == 12
-    BOTH(12, 4, 1, 4), BOTH(12, 4, 2, 4), BOTH(12, 4, 4, 4),
+    BOTH(12, 4, 1, 4), BOTH(12, 4, 2, 4), BOTH(12, 4, 4, 4), BOTH_TC(12, 1, 4),
 #elif AIDAX_VARIANT_H == 16
-    BOTH(16, 16, 1, 4), BOTH(16, 16, 4, 4), BOTH(16, 8, 8, 4),
+    BOTH(16, 16, 1, 4), BOTH(16, 16, 4, 4), BOTH(16, 8, 8, 4), BOTH_TC(16, 1, 4),
 #elif AIDAX_VARIANT_H == 20
-    BOTH(20, 4, 1, 4), BOTH(20, 4, 2, 4), BOTH(20, 4, 4, 4),
+    BOTH(20, 4, 1, 4), BOTH(20, 4, 2, 4), BOTH(20, 4, 4, 4), BOTH_TC(20, 1, 3),
 #elif AIDAX_VARIANT_H == 24
-    BOTH(24, 8, 1, 4), BOTH(24, 8, 4, 4), BOTH(24, 8, 8, 4),
+    BOTH(24, 8, 1, 4), BOTH(24, 8, 4, 4), BOTH(24, 8, 8, 4), BOTH_TC(24, 1, 3),
 #elif AIDAX_VARIANT_H == 32
-    BOTH(32, 32, 1, 4), BOTH(32, 16, 4, 4), BOTH(32, 8, 4, 4),
+    BOTH(32, 32, 1, 4), BOTH(32, 16, 4, 4), BOTH(32, 8, 4, 4), BOTH_TC(32, 2, 1),
 #elif AIDAX_VARIANT_H == 40
-    BOTH(40, 8, 1, 4), BOTH(40, 8, 2, 4), BOTH(40, 8, 4, 4),
+    BOTH(40, 8, 1, 4), BOTH(40, 8, 2, 4), BOTH(40, 8, 4, 4), BOTH_TC(40, 2, 1),
 #elif AIDAX_VARIANT_H == 64
     BOTH(64, 32, 1, 4), BOTH(64, 32, 4, 4), BOTH(64, 16, 4, 4),
 #elif AIDAX_VARIANT_H == 80

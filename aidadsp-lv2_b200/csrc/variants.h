@@ -11,6 +11,9 @@ struct KernelVariant {
     int ws;     // streams per warp
     const void* fn[2]; // [math_mode] kernel entry (for cudaFuncSetAttribute / cudaLaunchKernel)
     int (*warp_smem_floats)(int ts, int n_param_tiles);
+    int kind;             // 0 = FP32 register-tiled recurrence (kernels.cuh), 1 = tcgen05 tensor-core recurrence (kernels_tc.cuh)
+    int fixed_smem_floats; // shared memory that does not scale with the sub-block length (weights / MMA operands)
+    int ctas_per_sm;      // residency the shared-memory budget is sized for
 };
 
 // defined in variants.cu, compiled once per -DAIDAX_VARIANT_H=<H>

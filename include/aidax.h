@@ -24,6 +24,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the C ABI is the only thing a library built with -fvisibility=hidden exports */
+#endif
 
 #define AIDAX_ABI_VERSION 1
 
@@ -107,8 +110,11 @@ int aidax_engine_destroy(aidax_engine* e);
 /* cudaStream_t (as void*) all engine work is enqueued on; for external event timing. */
 void* aidax_engine_cuda_stream(aidax_engine* e);
 
-/* Tuning: how streams are tiled onto warps.  mode 0 = auto (by stream count), 1 = latency
- * (many lanes per stream), 2 = throughput (register-tiled, many streams per warp).
+/* Tuning: which kernel variant renders a model family.  mode 0 = auto (by stream count: FP32 latency shape ->
+ * FP32 throughput shape -> tensor-core shape for families of >= 4096 streams, env AIDAX_TC_MIN_STREAMS),
+ * 1 = FP32 latency shape (many lanes per stream), 2 = FP32 throughput shape (register-tiled, many streams per
+ * warp), 3 = tcgen05 tensor-core shape (128 streams per tile, 3xTF32 gate contraction; hidden <= 40, falls back
+ * to mode 0's FP32 choice for hidden 64/80).
  * math: 0 = fast (MUFU ex2/rcp), 1 = precise (expf + IEEE division). */
 int aidax_engine_configure(aidax_engine* e, int tile_mode, int math_mode);
 
@@ -213,6 +219,9 @@ int aidax_measure_fp32_peak(int device, int millis, double* tflops_out);
 /* Number of kernel launches issued by the engine since creation (for bench accounting). */
 uint64_t aidax_engine_launch_count(aidax_engine* e);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

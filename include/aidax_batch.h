@@ -27,6 +27,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the C ABI is the only thing a library built with -fvisibility=hidden exports */
+#endif
 
 #define AIDAX_PLUGIN_URI "http://aidadsp.cc/plugins/aidadsp-bundle/rt-neural-generic"
 #define AIDAX_BATCH__interface AIDAX_PLUGIN_URI "#batch"
@@ -52,6 +55,9 @@ typedef struct AidaxBatchInterface {
 
 #define AIDAX_BATCH_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

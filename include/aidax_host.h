@@ -21,6 +21,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the C ABI is the only thing a library built with -fvisibility=hidden exports */
+#endif
 
 typedef struct aidax_host aidax_host;
 
@@ -61,6 +64,9 @@ int aidax_host_save_state(aidax_host* h, int instance, char* path_out, int path_
 /* state:interface restore with the given path. */
 int aidax_host_restore_state(aidax_host* h, int instance, const char* path);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

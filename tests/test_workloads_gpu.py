@@ -26,7 +26,8 @@ def _oracle_stream(wl, s, n):
     return o
 
 
-@pytest.mark.parametrize("name,n,tile_mode", [("c2", 96, 0), ("c2", 1024, 0), ("c3", 256, 0), ("c4", 640, 0), ("c4", 2048, 2), ("c5", 200, 2)])
+@pytest.mark.parametrize("name,n,tile_mode", [("c2", 96, 0), ("c2", 1024, 0), ("c3", 256, 0), ("c4", 640, 0), ("c4", 2048, 2), ("c5", 200, 2),
+                                              ("c2", 1024, 3), ("c3", 300, 3), ("c4", 2048, 3), ("c5", 200, 3)])
 def test_config_vs_oracle_subset(native_libs, name, n, tile_mode):
     wl = workloads.get(name, n)
     eng = ax.Engine(max_streams=n, max_block=T)

@@ -18,11 +18,17 @@ def run(n_streams, hidden, cell=0, tile_mode=0, iters=20, input_size=1, eq=True)
     for _ in range(3):
         eng.render_device(x.data_ptr(), y.data_ptr(), n_streams, 128)
     eng.synchronize()
+    ext = torch.cuda.ExternalStream(eng.cuda_stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    e0.record(ext)
     for _ in range(iters):
         eng.render_device(x.data_ptr(), y.data_ptr(), n_streams, 128)
+    e1.record(ext)
     eng.synchronize()
-    dt = (time.perf_counter() - t0) / iters
+    wall = (time.perf_counter() - t0) / iters
+    dt = e0.elapsed_time(e1) * 1e-3 / iters
+    print("  (wall %.1f us/call)" % (wall * 1e6), end="")
     sps = n_streams * 128 / dt
     print("N=%7d H=%2d cell=%d in=%d tile=%d: %8.1f us/buffer  %.3e samples/s  = %8.0f RT streams  (%.2f TFLOP/s model)" % (
         n_streams, hidden, cell, input_size, tile_mode, dt * 1e6, sps, sps / 48000, sps * (8 * hidden * (hidden + input_size) + 10 * hidden + 1) / 1e12), flush=True)

@@ -12,7 +12,7 @@
 
 using namespace aidax::tc;
 
-__global__ void __launch_bounds__(128) probe_kernel(const float* A, const float* B, float* D, int N, int KP, int swap_fields, int split)
+__global__ void __launch_bounds__(128) probe_kernel(const float* A, const float* B, float* D, int N, int KP, int swap_fields, int split, int four, int rnd)
 {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* A, const float*
     for (int k = 0; k < KP; ++k) {
         float hi, lo;
         split_tf32(A[r * KP + k], hi, lo);
+        if (rnd) lo = __uint_as_float((__float_as_uint(lo) + 0x1000u) & 0xFFFFE000u);
         if (!split) { hi = A[r * KP + k]; lo = 0.f; }
         Ah[(k / 4) * 512 + r * 4 + (k % 4)] = hi;
         Al[(k / 4) * 512 + r * 4 + (k % 4)] = lo;
@@ -33,6 +34,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* A, const float*
         const int n = idx % N, k = idx / N;
         float hi, lo;
         split_tf32(B[n * KP + k], hi, lo);
+        if (rnd) lo = __uint_as_float((__float_as_uint(lo) + 0x1000u) & 0xFFFFE000u);
         if (!split) { hi = B[n * KP + k]; lo = 0.f; }
         Bh[(k / 4) * N * 4 + n * 4 + (k % 4)] = hi;
         Bl[(k / 4) * N * 4 + n * 4 + (k % 4)] = lo;
@@ -56,6 +58,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* A, const float*
                 return swap_fields ? make_smem_desc(smem_u32(base) + off, sbo, lbo) : make_smem_desc(smem_u32(base) + off, lbo, sbo);
             };
             if (split) {
+                if (four) { mma_tf32(tmem, desc(Al, ao, lbo_a), desc(Bl, bo, lbo_b), idesc, acc); acc = 1; }
                 mma_tf32(tmem, desc(Al, ao, lbo_a), desc(Bh, bo, lbo_b), idesc, acc); acc = 1;
                 mma_tf32(tmem, desc(Ah, ao, lbo_a), desc(Bl, bo, lbo_b), idesc, acc);
             }
@@ -96,23 +99,24 @@ int main()
         cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
         const size_t smem = (size_t)(2 * 128 * KP + 2 * N * KP) * 4;
         cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        for (int mode = 0; mode < 3; ++mode) {   // 0: lbo=K stride, split ; 1: fields swapped, split ; 2: lbo=K stride, single tf32
-            if ((mode == 1) != (pass == 1)) continue;
+        for (int mode = 0; mode < 6; ++mode) {   // 0: lbo=K stride, split ; 1: fields swapped, split ; 2: lbo=K stride, single tf32
+            if ((mode == 1) != (pass == 1)) continue;  // 3: four products ; 4: lo rounded to nearest ; 5: both
             cudaMemset(dD, 0xff, D.size() * 4);
-            probe_kernel<<<1, 128, smem>>>(dA, dB, dD, N, KP, mode == 1, mode != 2);
+            probe_kernel<<<1, 128, smem>>>(dA, dB, dD, N, KP, mode == 1, mode != 2, mode == 3 || mode == 5, mode >= 4);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("H=%d mode=%d CUDA error: %s\n", H, mode, cudaGetErrorString(e)); return 2; }
             cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
-            double worst = 0;
+            double worst = 0, sq = 0;
             for (int r = 0; r < 128; ++r)
                 for (int n = 0; n < N; ++n) {
                     double ref = 0;
                     for (int k = 0; k < KP; ++k) ref += (double)A[r * KP + k] * (double)B[n * KP + k];
                     const double d = fabs(ref - (double)D[r * N + n]);
                     if (!(d <= worst)) worst = d;   // NaN-propagating max
+                    sq += d * d;
                 }
-            printf("H=%2d N=%3d K=%2d mode=%d (%s) max abs err %.3g\n", H, N, KP, mode,
-                   mode == 0 ? "lbo=K-stride, 3xTF32" : mode == 1 ? "lbo/sbo swapped, 3xTF32" : "lbo=K-stride, 1xTF32", worst);
+            const char* names[] = {"lbo=K-stride, 3xTF32", "lbo/sbo swapped, 3xTF32", "lbo=K-stride, 1xTF32", "4 products", "3 products, lo rounded", "4 products, lo rounded"};
+            printf("H=%2d N=%3d K=%2d mode=%d (%s) max abs err %.3g rms %.3g\n", H, N, KP, mode, names[mode], worst, sqrt(sq / (128.0 * N)));
             if (mode == 0 && !(worst < 1e-5)) bad = 1;
         }
         cudaFree(dA); cudaFree(dB); cudaFree(dD);
