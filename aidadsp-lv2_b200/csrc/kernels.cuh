@@ -228,6 +228,17 @@ __device__ __forceinline__ void load_tile(float* xbuf, const RenderParams& p, co
             const float* src = p.in + (size_t)(slot - p.first_stream) * p.stride + t0;
             for (int t = lane; t < ts; t += 32) xbuf[t * XP + j] = __ldg(src + t);
         }
+    } else if constexpr (WS == 32) { // interleaved [n][stream], one stream per lane: 8 rows of loads in flight per round
+        const int slot = wslots[lane];
+        const float* src = p.in + (size_t)t0 * p.stride + (slot - p.first_stream);
+        for (int t = 0; t < ts; t += 8) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = (slot >= 0 && t + i < ts) ? __ldg(src + (size_t)(t + i) * p.stride) : 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (t + i < ts) xbuf[(t + i) * XP + lane] = v[i];
+        }
     } else { // interleaved [n][stream]
         for (int idx = lane; idx < ts * WS; idx += 32) {
             const int t = idx / WS, j = idx - t * WS;

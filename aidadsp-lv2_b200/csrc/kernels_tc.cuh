@@ -113,9 +113,17 @@ struct TcCell {
         const float rab = r * cd, rcd = r * ab;
         ia = rab * b; ib = rab * a; ic = rcd * d; id = rcd * c;
     }
-    // 1 + exp(s*x), exponent clamped so that four of them can be multiplied without overflow
+    // 1 + 2^e, exponent clamped so that four of them can be multiplied without overflow
     // (sigmoid(-16.6) = 6e-8, 1 - tanh(8.3) = 1.2e-7: the clamp is below fp32 resolution of the results)
-    __device__ __forceinline__ static float one_plus_exp(float x, float s_log2e) { return 1.0f + ex2_approx(fminf(x * s_log2e, 24.0f)); }
+    __device__ __forceinline__ static float one_plus_exp2(float e) { return 1.0f + ex2_approx(fminf(e, 24.0f)); }
+    // In fast-math mode the B operand's columns are pre-scaled so that the accumulator IS that exponent:
+    // sigmoid(x) = 1/(1 + 2^(-x log2 e)), tanh(x) = 1 - 2/(1 + 2^(2x log2 e)).  Column order per unit: LSTM i,f,g,o;
+    // GRU z, r, Uh.h+bh1, Wh.x+bh0 (the last two are summed as r*a2 + a3 before the tanh, so both carry its scale).
+    __host__ __device__ static constexpr float column_scale(int g)
+    {
+        constexpr float L2E = 1.4426950408889634f;
+        return CELL == 0 ? (g == 2 ? 2.f * L2E : -L2E) : (g < 2 ? -L2E : 2.f * L2E);
+    }
 
     // state: cst (LSTM: c, GRU: h) in registers for the whole render call, h(t-1) split hi/lo in the A operand tile
     __device__ __forceinline__ static void load_state(const TcTile& tt, float (&cst)[H], const StreamArrays& sa, int slot, bool load)
@@ -138,26 +146,40 @@ struct TcCell {
             store_chunk(tt, q, hv[0], hv[1], hv[2], hv[3]);
         }
     }
-    __device__ __forceinline__ static void store_state(const float (&cst)[H], const StreamArrays& sa, int slot)
+    // LSTM: h is read back from the A operand tile as hi + (lo as the tensor core sees it): exactly the value the
+    // next step would have used, so a render call split into two periods gives the same samples as one long call.
+    __device__ __forceinline__ static void store_state(const TcTile& tt, const float (&cst)[H], const StreamArrays& sa, int slot)
     {
         const size_t cap = (size_t)sa.cap;
 #pragma unroll
-        for (int u = 0; u < H; ++u) {
-            if (CELL == 0) sa.rnn[(size_t)(kMaxHidden + u) * cap + slot] = cst[u];
-            else sa.rnn[(size_t)u * cap + slot] = cst[u];
+        for (int q = 0; q < H / 4; ++q) {
+            float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
+            if (CELL == 0) {
+                hi = *reinterpret_cast<const float4*>(tt.a_hi + q * 512);
+                lo = *reinterpret_cast<const float4*>(tt.a_lo + q * 512);
+            }
+            const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int u = 4 * q + i;
+                if (CELL == 0) {
+                    sa.rnn[(size_t)(kMaxHidden + u) * cap + slot] = cst[u];
+                    sa.rnn[(size_t)u * cap + slot] = hv[i] + __uint_as_float(__float_as_uint(lv[i]) & 0xFFFFE000u);
+                } else {
+                    sa.rnn[(size_t)u * cap + slot] = cst[u];
+                }
+            }
         }
     }
 
     // n steps of the cell for this thread's stream.  xcol: the stream's column in the audio tile (nullptr = zero input,
     // pre-warm); p1col/p2col: param columns or nullptr (then p1c/p2c).  Every thread of the tile must call this
-    // with the same n.  commit: write y into the audio tile; store_h: also write h of the last step to the state
-    // arrays (LSTM; c and the GRU h are written by store_state).
+    // with the same n.  commit: write y into the audio tile.
     __device__ static void run(TcTile& tt, float (&cst)[H], float* xcol, const float* p1col, const float* p2col, float p1c, float p2c, int n,
-                               float in_gain, float out_gain, bool in_skip, const StreamArrays& sa, int slot, bool commit, bool store_h)
+                               float in_gain, float out_gain, bool in_skip, bool commit)
     {
         constexpr int XP = S::XP;
         constexpr float L2E = 1.4426950408889634f;
-        const size_t cap = (size_t)sa.cap;
         const float db = tt.dw[H];
 
         for (int t = 0; t < n; ++t) {
@@ -178,7 +200,6 @@ struct TcCell {
             tt.phase ^= 1u;
             tc::tc_fence_after();
 
-            const bool last = store_h && t == n - 1;
             float y0 = db, y1 = 0.f;
             uint32_t raw[16];
             tc::tmem_ld16(tt.tmem_ld, raw);
@@ -197,11 +218,11 @@ struct TcCell {
                     for (int i = 0; i < 4; ++i) {
                         const int u = 4 * q + i;
                         float ii, fi, gi;
-                        inv4(one_plus_exp(a[4 * i], -L2E), one_plus_exp(a[4 * i + 1], -L2E), one_plus_exp(a[4 * i + 2], 2.f * L2E),
-                             one_plus_exp(a[4 * i + 3], -L2E), ii, fi, gi, og[i]);
+                        inv4(one_plus_exp2(a[4 * i]), one_plus_exp2(a[4 * i + 1]), one_plus_exp2(a[4 * i + 2]), one_plus_exp2(a[4 * i + 3]),
+                             ii, fi, gi, og[i]);
                         const float c = fmaf(ii, fmaf(-2.f, gi, 1.f), fi * cst[u]);
                         cst[u] = c;
-                        e4[i] = one_plus_exp(c, 2.f * L2E);
+                        e4[i] = one_plus_exp2(c * (2.f * L2E));
                     }
                     float t0, t1, t2, t3;
                     inv4(e4[0], e4[1], e4[2], e4[3], t0, t1, t2, t3);
@@ -215,10 +236,10 @@ struct TcCell {
 #pragma unroll
                     for (int i = 0; i < 4; i += 2) {
                         float r0, r1;
-                        inv4(one_plus_exp(a[4 * i], -L2E), one_plus_exp(a[4 * i + 1], -L2E), one_plus_exp(a[4 * i + 4], -L2E),
-                             one_plus_exp(a[4 * i + 5], -L2E), z[i], r0, z[i + 1], r1);
-                        e4[i] = one_plus_exp(fmaf(r0, a[4 * i + 2], a[4 * i + 3]), 2.f * L2E);
-                        e4[i + 1] = one_plus_exp(fmaf(r1, a[4 * i + 6], a[4 * i + 7]), 2.f * L2E);
+                        inv4(one_plus_exp2(a[4 * i]), one_plus_exp2(a[4 * i + 1]), one_plus_exp2(a[4 * i + 4]), one_plus_exp2(a[4 * i + 5]),
+                             z[i], r0, z[i + 1], r1);
+                        e4[i] = one_plus_exp2(fmaf(r0, a[4 * i + 2], a[4 * i + 3]));
+                        e4[i + 1] = one_plus_exp2(fmaf(r1, a[4 * i + 6], a[4 * i + 7]));
                     }
                     float t4[4];
                     inv4(e4[0], e4[1], e4[2], e4[3], t4[0], t4[1], t4[2], t4[3]);
@@ -250,7 +271,6 @@ struct TcCell {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int u = 4 * q + i;
-                    if (CELL == 0 && last) sa.rnn[(size_t)u * cap + slot] = hn[i];
                     if (i & 1) y1 = fmaf(tt.dw[u], hn[i], y1);
                     else y0 = fmaf(tt.dw[u], hn[i], y0);
                 }
@@ -304,6 +324,7 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
             float w = 0.f;
             if (k < H + 3) w = __ldg(wk + (size_t)k * S::N + n);
             else if (k == H + 3) w = __ldg(bias + n);
+            if (MATH == 0) w *= Cell::column_scale(n & 3); // the accumulator is directly the exponent of 2 the gate needs
             float hi, lo;
             tc::split_tf32(w, hi, lo);
             const int off = (k >> 2) * (S::N * 4) + n * 4 + (k & 3);
@@ -362,9 +383,8 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
         const float p1c = sa.p_mem[slot], p2c = sa.p_mem[(size_t)sa.cap + slot];
         float cst[H];
         Cell::load_state(tt, cst, sa, slot, false);
-        Cell::run(tt, cst, nullptr, nullptr, nullptr, p1c, p2c, kPrewarmSteps, md.in_gain, md.out_gain, md.in_skip != 0, sa, slot,
-                  false, want_prewarm);
-        if (want_prewarm) Cell::store_state(cst, sa, slot);
+        Cell::run(tt, cst, nullptr, nullptr, nullptr, p1c, p2c, kPrewarmSteps, md.in_gain, md.out_gain, md.in_skip != 0, false);
+        if (want_prewarm) Cell::store_state(tt, cst, sa, slot);
     }
 
     uint32_t flags = 0, dfl = 0;
@@ -404,7 +424,7 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
         // ---- the network
         if (any_net)
             Cell::run(tt, cst, xbuf + lane, p1buf ? p1buf + lane : nullptr, p2buf ? p2buf + lane : nullptr, 0.f, 0.f, ts, md.in_gain,
-                      md.out_gain, md.in_skip != 0, sa, slot, net_on, net_on && t0 + ts >= p.n_samples);
+                      md.out_gain, md.in_skip != 0, net_on);
 
         // ---- stages after the network (:645-655)
         if (cslot >= 0 && enabled) {
@@ -423,7 +443,7 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
         __syncwarp();
     }
 
-    if (net_on) Cell::store_state(cst, sa, slot);
+    if (net_on) Cell::store_state(tt, cst, sa, slot);
 
     tc::tc_fence_before();
     __syncthreads();

@@ -22,11 +22,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar_addr, uint32_t parity
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, P1;\n\t"
         "}"
         : "=r"(ok)
-        : "r"(bar_addr), "r"(parity)
+        : "r"(bar_addr), "r"(parity), "r"(0x989680u) /* suspend-time hint: park the warp instead of spinning on issue slots */
         : "memory");
     return ok != 0;
 }

