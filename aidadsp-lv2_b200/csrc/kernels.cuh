@@ -129,15 +129,37 @@ __device__ __forceinline__ void pass_eq(float* xcol, int ts, const StreamArrays&
     f2.load(sa, BQ_MID, slot);
     f3.load(sa, BQ_TREBLE, slot);
     f4.load(sa, BQ_PRESENCE, slot);
+    if (ts >= 5) {
+        // Software-pipelined over time: in one iteration stage k works on sample t-k, so the five double-precision
+        // recurrences (and their float<->double conversions) are independent instructions streams instead of one
+        // 5-deep dependent chain per sample.  Every filter still sees exactly its own input sequence: bit-identical.
+        float l0 = f0.process(xcol[0]);
+        float l1 = f1.process(l0); l0 = f0.process(xcol[XP]);
+        float l2 = f2.process(l1); l1 = f1.process(l0); l0 = f0.process(xcol[2 * XP]);
+        float l3 = f3.process(l2); l2 = f2.process(l1); l1 = f1.process(l0); l0 = f0.process(xcol[3 * XP]);
 #pragma unroll 2
-    for (int t = 0; t < ts; ++t) {
-        float x = xcol[t * XP];
-        x = f0.process(x);
-        x = f1.process(x);
-        x = f2.process(x);
-        x = f3.process(x);
-        x = f4.process(x);
-        xcol[t * XP] = x;
+        for (int t = 4; t < ts; ++t) {
+            const float o = f4.process(l3);
+            l3 = f3.process(l2);
+            l2 = f2.process(l1);
+            l1 = f1.process(l0);
+            l0 = f0.process(xcol[t * XP]);
+            xcol[(t - 4) * XP] = o;
+        }
+        xcol[(ts - 4) * XP] = f4.process(l3); l3 = f3.process(l2); l2 = f2.process(l1); l1 = f1.process(l0);
+        xcol[(ts - 3) * XP] = f4.process(l3); l3 = f3.process(l2); l2 = f2.process(l1);
+        xcol[(ts - 2) * XP] = f4.process(l3); l3 = f3.process(l2);
+        xcol[(ts - 1) * XP] = f4.process(l3);
+    } else {
+        for (int t = 0; t < ts; ++t) {
+            float x = xcol[t * XP];
+            x = f0.process(x);
+            x = f1.process(x);
+            x = f2.process(x);
+            x = f3.process(x);
+            x = f4.process(x);
+            xcol[t * XP] = x;
+        }
     }
     f0.store(sa, BQ_DEPTH, slot);
     f1.store(sa, BQ_BASS, slot);

@@ -172,6 +172,72 @@ struct TcCell {
         }
     }
 
+    // gate nonlinearities + cell update of the 4 hidden units whose 16 accumulator columns are in `raw`
+    __device__ __forceinline__ static void eval_chunk(const uint32_t (&raw)[16], int q, float (&cst)[H], float (&hn)[4])
+    {
+        constexpr float L2E = 1.4426950408889634f;
+        float a[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(raw[i]);
+        if (MATH == 0 && CELL == 0) {
+            // LSTM, RTN/lstm/lstm_xsimd.h:193-213, 271-283: c' = i*tanh(g) + f*c ; h' = o*tanh(c')
+            float og[4], e4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int u = 4 * q + i;
+                float ii, fi, gi;
+                inv4(one_plus_exp2(a[4 * i]), one_plus_exp2(a[4 * i + 1]), one_plus_exp2(a[4 * i + 2]), one_plus_exp2(a[4 * i + 3]),
+                     ii, fi, gi, og[i]);
+                const float c = fmaf(ii, fmaf(-2.f, gi, 1.f), fi * cst[u]);
+                cst[u] = c;
+                e4[i] = one_plus_exp2(c * (2.f * L2E));
+            }
+            float t0, t1, t2, t3;
+            inv4(e4[0], e4[1], e4[2], e4[3], t0, t1, t2, t3);
+            hn[0] = og[0] * fmaf(-2.f, t0, 1.f);
+            hn[1] = og[1] * fmaf(-2.f, t1, 1.f);
+            hn[2] = og[2] * fmaf(-2.f, t2, 1.f);
+            hn[3] = og[3] * fmaf(-2.f, t3, 1.f);
+        } else if (MATH == 0) {
+            // GRU, RTN/gru/gru_xsimd.h:219-239, 265-271: h' = (1-z)*tanh(r*(Uh.h+bh1) + Wh.x+bh0) + z*h
+            float z[4], e4[4];
+#pragma unroll
+            for (int i = 0; i < 4; i += 2) {
+                float r0, r1;
+                inv4(one_plus_exp2(a[4 * i]), one_plus_exp2(a[4 * i + 1]), one_plus_exp2(a[4 * i + 4]), one_plus_exp2(a[4 * i + 5]),
+                     z[i], r0, z[i + 1], r1);
+                e4[i] = one_plus_exp2(fmaf(r0, a[4 * i + 2], a[4 * i + 3]));
+                e4[i + 1] = one_plus_exp2(fmaf(r1, a[4 * i + 6], a[4 * i + 7]));
+            }
+            float t4[4];
+            inv4(e4[0], e4[1], e4[2], e4[3], t4[0], t4[1], t4[2], t4[3]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int u = 4 * q + i;
+                const float hh = fmaf(-2.f, t4[i], 1.f);
+                hn[i] = fmaf(1.0f - z[i], hh, z[i] * cst[u]);
+                cst[u] = hn[i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int u = 4 * q + i;
+                if (CELL == 0) {
+                    const float ig = sigmoid_f<1>(a[4 * i]), fg = sigmoid_f<1>(a[4 * i + 1]);
+                    const float gg = tanh_f<1>(a[4 * i + 2]), og = sigmoid_f<1>(a[4 * i + 3]);
+                    const float c = fmaf(ig, gg, fg * cst[u]);
+                    cst[u] = c;
+                    hn[i] = og * tanh_f<1>(c);
+                } else {
+                    const float zg = sigmoid_f<1>(a[4 * i]), rg = sigmoid_f<1>(a[4 * i + 1]);
+                    const float hh = tanh_f<1>(fmaf(rg, a[4 * i + 2], a[4 * i + 3]));
+                    hn[i] = fmaf(1.0f - zg, hh, zg * cst[u]);
+                    cst[u] = hn[i];
+                }
+            }
+        }
+    }
+
     // n steps of the cell for this thread's stream.  xcol: the stream's column in the audio tile (nullptr = zero input,
     // pre-warm); p1col/p2col: param columns or nullptr (then p1c/p2c).  Every thread of the tile must call this
     // with the same n.  commit: write y into the audio tile.
@@ -179,7 +245,6 @@ struct TcCell {
                                float in_gain, float out_gain, bool in_skip, bool commit)
     {
         constexpr int XP = S::XP;
-        constexpr float L2E = 1.4426950408889634f;
         const float db = tt.dw[H];
 
         for (int t = 0; t < n; ++t) {
@@ -200,81 +265,30 @@ struct TcCell {
             tt.phase ^= 1u;
             tc::tc_fence_after();
 
+            // epilogue: groups of two 16-column chunks (8 hidden units) are loaded together and evaluated as one
+            // straight-line block, so the 8 + 2 batched reciprocal chains of a group overlap each other's MUFU latency
             float y0 = db, y1 = 0.f;
-            uint32_t raw[16];
-            tc::tmem_ld16(tt.tmem_ld, raw);
 #pragma unroll
-            for (int q = 0; q < H / 4; ++q) {
-                tc::tmem_ld_wait16(raw);
-                float a[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(raw[i]);
-                if (q + 1 < H / 4) tc::tmem_ld16(tt.tmem_ld + 16 * (q + 1), raw); // in flight while this chunk is evaluated
-                float hn[4];
-                if (MATH == 0 && CELL == 0) {
-                    // LSTM, RTN/lstm/lstm_xsimd.h:193-213, 271-283: c' = i*tanh(g) + f*c ; h' = o*tanh(c')
-                    float og[4], e4[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int u = 4 * q + i;
-                        float ii, fi, gi;
-                        inv4(one_plus_exp2(a[4 * i]), one_plus_exp2(a[4 * i + 1]), one_plus_exp2(a[4 * i + 2]), one_plus_exp2(a[4 * i + 3]),
-                             ii, fi, gi, og[i]);
-                        const float c = fmaf(ii, fmaf(-2.f, gi, 1.f), fi * cst[u]);
-                        cst[u] = c;
-                        e4[i] = one_plus_exp2(c * (2.f * L2E));
-                    }
-                    float t0, t1, t2, t3;
-                    inv4(e4[0], e4[1], e4[2], e4[3], t0, t1, t2, t3);
-                    hn[0] = og[0] * fmaf(-2.f, t0, 1.f);
-                    hn[1] = og[1] * fmaf(-2.f, t1, 1.f);
-                    hn[2] = og[2] * fmaf(-2.f, t2, 1.f);
-                    hn[3] = og[3] * fmaf(-2.f, t3, 1.f);
-                } else if (MATH == 0) {
-                    // GRU, RTN/gru/gru_xsimd.h:219-239, 265-271: h' = (1-z)*tanh(r*(Uh.h+bh1) + Wh.x+bh0) + z*h
-                    float z[4], e4[4];
-#pragma unroll
-                    for (int i = 0; i < 4; i += 2) {
-                        float r0, r1;
-                        inv4(one_plus_exp2(a[4 * i]), one_plus_exp2(a[4 * i + 1]), one_plus_exp2(a[4 * i + 4]), one_plus_exp2(a[4 * i + 5]),
-                             z[i], r0, z[i + 1], r1);
-                        e4[i] = one_plus_exp2(fmaf(r0, a[4 * i + 2], a[4 * i + 3]));
-                        e4[i + 1] = one_plus_exp2(fmaf(r1, a[4 * i + 6], a[4 * i + 7]));
-                    }
-                    float t4[4];
-                    inv4(e4[0], e4[1], e4[2], e4[3], t4[0], t4[1], t4[2], t4[3]);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int u = 4 * q + i;
-                        const float hh = fmaf(-2.f, t4[i], 1.f);
-                        hn[i] = fmaf(1.0f - z[i], hh, z[i] * cst[u]);
-                        cst[u] = hn[i];
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int u = 4 * q + i;
-                        if (CELL == 0) {
-                            const float ig = sigmoid_f<1>(a[4 * i]), fg = sigmoid_f<1>(a[4 * i + 1]);
-                            const float gg = tanh_f<1>(a[4 * i + 2]), og = sigmoid_f<1>(a[4 * i + 3]);
-                            const float c = fmaf(ig, gg, fg * cst[u]);
-                            cst[u] = c;
-                            hn[i] = og * tanh_f<1>(c);
-                        } else {
-                            const float zg = sigmoid_f<1>(a[4 * i]), rg = sigmoid_f<1>(a[4 * i + 1]);
-                            const float hh = tanh_f<1>(fmaf(rg, a[4 * i + 2], a[4 * i + 3]));
-                            hn[i] = fmaf(1.0f - zg, hh, zg * cst[u]);
-                            cst[u] = hn[i];
-                        }
-                    }
+            for (int q = 0; q < H / 4; q += 2) {
+                constexpr int NQ = H / 4;
+                const bool two = q + 1 < NQ;
+                uint32_t raw0[16], raw1[16];
+                tc::tmem_ld16(tt.tmem_ld + 16 * q, raw0);
+                if (two) tc::tmem_ld16(tt.tmem_ld + 16 * (q + 1), raw1);
+                tc::tmem_ld_wait16(raw0);
+                float hn0[4], hn1[4];
+                eval_chunk(raw0, q, cst, hn0);
+                if (two) {
+                    tc::tmem_ld_wait16(raw1); // already complete (one wait covers all outstanding loads); keeps the asm ordering explicit
+                    eval_chunk(raw1, q + 1, cst, hn1);
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int u = 4 * q + i;
-                    if (i & 1) y1 = fmaf(tt.dw[u], hn[i], y1);
-                    else y0 = fmaf(tt.dw[u], hn[i], y0);
+                    y0 = fmaf(tt.dw[4 * q + i], hn0[i], y0);
+                    if (two) y1 = fmaf(tt.dw[4 * q + 4 + i], hn1[i], y1);
                 }
-                store_chunk(tt, q, hn[0], hn[1], hn[2], hn[3]);
+                store_chunk(tt, q, hn0[0], hn0[1], hn0[2], hn0[3]);
+                if (two) store_chunk(tt, q + 1, hn1[0], hn1[1], hn1[2], hn1[3]);
             }
             // dense + skip + output gain (applyModel, rt-neural-generic.cpp:170-182)
             if (xcol && commit) {
