@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -182,6 +183,7 @@ struct aidax_host {
     LV2_URID u_sequence = 0, u_object = 0, u_urid = 0, u_path = 0, u_patch_set = 0, u_patch_property = 0, u_patch_value = 0, u_json = 0;
     std::unique_ptr<Pool> pool;
     std::atomic<bool> any_scheduled{false};
+    double t_run = 0.0, t_end = 0.0, n_periods = 0.0;
 };
 
 namespace {
@@ -420,6 +422,11 @@ void aidax_host_close(aidax_host* h)
 int aidax_host_n_instances(const aidax_host* h) { return h ? h->n : 0; }
 int aidax_host_is_batched(const aidax_host* h) { return h && h->batch ? 1 : 0; }
 uint64_t aidax_host_launch_count(const aidax_host* h) { return h && h->batch ? h->batch->launch_count() : 0; }
+void aidax_host_timing(const aidax_host* h, double out[3])
+{
+    if (!h || !out) return;
+    out[0] = h->t_run; out[1] = h->t_end; out[2] = h->n_periods;
+}
 float* aidax_host_input(aidax_host* h) { return h ? h->in : nullptr; }
 float* aidax_host_output(aidax_host* h) { return h ? h->out : nullptr; }
 size_t aidax_host_stride(const aidax_host* h) { return h ? h->stride : 0; }
@@ -465,15 +472,21 @@ int aidax_host_run(aidax_host* h, int n_samples)
     const int nt = h->pool->size();
     const int n = h->n;
     int rc = 0;
+    const auto t0 = std::chrono::steady_clock::now();
     if (h->batch) h->batch->begin();
     h->pool->run([&](int w) {
         const int lo = (int)((int64_t)n * w / nt), hi = (int)((int64_t)n * (w + 1) / nt);
         run_instances(h, lo, hi, (uint32_t)n_samples);
     });
+    const auto t1 = std::chrono::steady_clock::now();
     if (h->batch) {
         rc = h->batch->end();
         if (rc) set_err("batch end failed: %s", h->batch->last_error());
     }
+    const auto t2 = std::chrono::steady_clock::now();
+    h->t_run += std::chrono::duration<double>(t1 - t0).count();
+    h->t_end += std::chrono::duration<double>(t2 - t1).count();
+    h->n_periods += 1.0;
     if (h->any_scheduled.load(std::memory_order_relaxed)) {
         h->any_scheduled.store(false, std::memory_order_relaxed);
         h->pool->run([&](int w) {

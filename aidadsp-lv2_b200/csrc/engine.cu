@@ -74,6 +74,14 @@ struct LaunchPlan {
     int max_param_tiles = 0;
 };
 
+// the launches that render one stream range [first, first + n): block -> (model, slots) tables on the device
+struct RangePlan {
+    uint64_t epoch = 0;
+    int tile_mode = -1;
+    std::vector<LaunchPlan> launches;
+    DevArray<int> d_tables;
+};
+
 } // namespace aidax
 
 using namespace aidax;
@@ -110,7 +118,6 @@ struct aidax_engine {
     DevArray<double> d_bq_coef, d_bq_z;
     DevArray<float> d_io_in, d_io_out;
     DevArray<ModelDev> d_models;
-    DevArray<int> d_tables;
     std::vector<int> h_tables;
 
     std::vector<ModelEntry> models;
@@ -119,10 +126,12 @@ struct aidax_engine {
 
     std::vector<Family> families;
     // plan cache
-    uint64_t membership_epoch = 1, plan_epoch = 0;
-    int plan_first = -1, plan_n = -1, plan_tile_mode = -1;
-    std::vector<LaunchPlan> plan;
+    uint64_t membership_epoch = 1;
+    std::map<std::pair<int, int>, RangePlan> plans; // keyed by (first, n); the pipelined host path renders in chunks
     std::vector<const void*> attr_done;
+    // pipelined host rendering: copy-in / copy-out streams and per-chunk events
+    cudaStream_t stream_in = nullptr, stream_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_done;
 
     StreamArrays sa() const
     {
@@ -273,10 +282,17 @@ static const KernelVariant* choose_variant(const aidax_engine* e, const Family& 
     return v.front();
 }
 
-static int build_plan(aidax_engine* e, int first, int n)
+static int build_plan(aidax_engine* e, int first, int n, RangePlan** out)
 {
-    if (e->plan_epoch == e->membership_epoch && e->plan_first == first && e->plan_n == n && e->plan_tile_mode == e->tile_mode) return AIDAX_OK;
-    e->plan.clear();
+    if (e->plans.size() > 256) { // ranges come and go (chunk sizes change): drop stale tables
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        for (auto& kv : e->plans) kv.second.d_tables.release();
+        e->plans.clear();
+    }
+    RangePlan& rp = e->plans[std::make_pair(first, n)];
+    *out = &rp;
+    if (rp.epoch == e->membership_epoch && rp.tile_mode == e->tile_mode) return AIDAX_OK;
+    rp.launches.clear();
     e->h_tables.clear();
     const int last = std::min(first + n, e->n_open_hi);
     for (const Family& fam : e->families) {
@@ -311,21 +327,19 @@ static int build_plan(aidax_engine* e, int first, int n)
         e->h_tables.insert(e->h_tables.end(), blk_model.begin(), blk_model.end());
         lp.tbl_offset_slots = e->h_tables.size();
         e->h_tables.insert(e->h_tables.end(), blk_slots.begin(), blk_slots.end());
-        e->plan.push_back(lp);
+        rp.launches.push_back(lp);
     }
-    if (e->d_tables.n < e->h_tables.size()) {
+    if (rp.d_tables.n < e->h_tables.size()) {
         CUDA_TRY(cudaStreamSynchronize(e->stream));
-        e->d_tables.release();
-        CUDA_TRY(e->d_tables.alloc(e->h_tables.size() * 2 + 1024));
+        rp.d_tables.release();
+        CUDA_TRY(rp.d_tables.alloc(e->h_tables.size() * 2 + 1024));
     }
     if (!e->h_tables.empty()) {
         CUDA_TRY(cudaStreamSynchronize(e->stream)); // a previous launch may still read the old table
-        CUDA_TRY(cudaMemcpy(e->d_tables.d, e->h_tables.data(), e->h_tables.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(rp.d_tables.d, e->h_tables.data(), e->h_tables.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
-    e->plan_epoch = e->membership_epoch;
-    e->plan_first = first;
-    e->plan_n = n;
-    e->plan_tile_mode = e->tile_mode;
+    rp.epoch = e->membership_epoch;
+    rp.tile_mode = e->tile_mode;
     return AIDAX_OK;
 }
 
@@ -333,9 +347,10 @@ static int launch_all(aidax_engine* e, int first, int n, int n_samples, const fl
 {
     int rc = upload_dirty(e, first, n);
     if (rc) return rc;
-    rc = build_plan(e, first, n);
+    RangePlan* rp = nullptr;
+    rc = build_plan(e, first, n, &rp);
     if (rc) return rc;
-    for (const LaunchPlan& lp : e->plan) {
+    for (const LaunchPlan& lp : rp->launches) {
         const KernelVariant* kv = lp.kv;
         // samples per shared-memory sub-block: as many as fit with the variant's target residency, capped at the period
         int ts = n_samples;
@@ -352,8 +367,8 @@ static int launch_all(aidax_engine* e, int first, int n, int n_samples, const fl
         RenderParams p{};
         p.in = d_in; p.out = d_out; p.layout = layout; p.stride = (long long)stride; p.first_stream = first;
         p.n_samples = n_samples; p.ts = ts; p.math_mode = e->math_mode;
-        p.blk_model = e->d_tables.d + lp.tbl_offset_model;
-        p.blk_slots = e->d_tables.d + lp.tbl_offset_slots;
+        p.blk_model = rp->d_tables.d + lp.tbl_offset_model;
+        p.blk_slots = rp->d_tables.d + lp.tbl_offset_slots;
         p.models = e->d_models.d;
         p.sa = e->sa();
         void* args[] = {&p};
@@ -416,6 +431,8 @@ int aidax_engine_create(int device, int max_streams, int max_block, aidax_engine
     e->smem_per_sm = prop.sharedMemPerMultiprocessor;
     if (const char* v = std::getenv("AIDAX_TC_MIN_STREAMS")) e->tc_min_streams = std::atoi(v);
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_out, cudaStreamNonBlocking));
     const size_t cap = (size_t)e->cap;
     e->streams.resize(cap);
     e->dirty_ctrl.assign(cap, 0); e->dirty_coef.assign(cap, 0); e->dirty_cmd.assign(cap, 0);
@@ -452,7 +469,12 @@ int aidax_engine_destroy(aidax_engine* e)
     e->d_exp_coef.release(); e->d_lin_denom.release(); e->d_pre_mem.release(); e->d_master_mem.release();
     e->d_p_mem.release(); e->d_p_step.release(); e->d_p_target.release(); e->d_rnn.release();
     e->d_bq_coef.release(); e->d_bq_z.release(); e->d_io_in.release(); e->d_io_out.release();
-    e->d_models.release(); e->d_tables.release();
+    e->d_models.release();
+    for (auto& kv : e->plans) kv.second.d_tables.release();
+    for (cudaEvent_t ev : e->ev_in) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->ev_done) cudaEventDestroy(ev);
+    if (e->stream_in) cudaStreamDestroy(e->stream_in);
+    if (e->stream_out) cudaStreamDestroy(e->stream_out);
     cudaStreamDestroy(e->stream);
     delete e;
     return AIDAX_OK;
@@ -788,16 +810,48 @@ int aidax_render_host(aidax_engine* e, int first_stream, int n_streams, int n_sa
     std::lock_guard<std::mutex> lk(e->mu);
     CUDA_TRY(cudaSetDevice(e->device));
     // Stage through the engine's device arena with a dense pitch (planar: n_samples, interleaved: n_streams)
-    const size_t rows = layout == AIDAX_LAYOUT_PLANAR ? (size_t)n_streams : (size_t)n_samples;
-    const size_t cols = layout == AIDAX_LAYOUT_PLANAR ? (size_t)n_samples : (size_t)n_streams;
-    if (stride < cols) return fail(AIDAX_ERR_ARG, "stride %zu smaller than row length %zu", stride, cols);
-    CUDA_TRY(cudaMemcpy2DAsync(e->d_io_in.d, cols * sizeof(float), in, stride * sizeof(float), cols * sizeof(float), rows,
-                               cudaMemcpyHostToDevice, e->stream));
-    rc = launch_all(e, first_stream, n_streams, n_samples, e->d_io_in.d, e->d_io_out.d, layout, cols);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpy2DAsync(out, stride * sizeof(float), e->d_io_out.d, cols * sizeof(float), cols * sizeof(float), rows,
-                               cudaMemcpyDeviceToHost, e->stream));
-    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (layout == AIDAX_LAYOUT_PLANAR ? stride < (size_t)n_samples : stride < (size_t)n_streams)
+        return fail(AIDAX_ERR_ARG, "stride %zu smaller than a row", stride);
+    // Large periods are cut into stream chunks that flow through three CUDA streams (copy in -> kernels -> copy
+    // out), so that on a PCIe-attached GPU the two copy directions and the kernels overlap; a small period is one chunk.
+    const size_t bytes = (size_t)n_streams * (size_t)n_samples * sizeof(float);
+    int n_chunks = (int)std::min<size_t>(8, std::max<size_t>(1, bytes / ((size_t)8 << 20)));
+    int chunk = (n_streams + n_chunks - 1) / n_chunks;
+    chunk = (chunk + 1023) & ~1023; // whole tiles of every kernel shape
+    n_chunks = (n_streams + chunk - 1) / chunk;
+    while ((int)e->ev_in.size() < n_chunks) {
+        cudaEvent_t a, b;
+        CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        e->ev_in.push_back(a);
+        e->ev_done.push_back(b);
+    }
+    const bool piped = n_chunks > 1;
+    cudaStream_t s_in = piped ? e->stream_in : e->stream, s_out = piped ? e->stream_out : e->stream;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int c0 = c * chunk, cn = std::min(chunk, n_streams - c0);
+        const size_t rows = layout == AIDAX_LAYOUT_PLANAR ? (size_t)cn : (size_t)n_samples;
+        const size_t cols = layout == AIDAX_LAYOUT_PLANAR ? (size_t)n_samples : (size_t)cn;
+        const size_t doff = (size_t)c0 * (size_t)n_samples; // chunks are dense, back to back in the arena
+        const float* src = layout == AIDAX_LAYOUT_PLANAR ? in + (size_t)c0 * stride : in + c0;
+        CUDA_TRY(cudaMemcpy2DAsync(e->d_io_in.d + doff, cols * sizeof(float), src, stride * sizeof(float), cols * sizeof(float), rows,
+                                   cudaMemcpyHostToDevice, s_in));
+        if (piped) {
+            CUDA_TRY(cudaEventRecord(e->ev_in[c], s_in));
+            CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_in[c], 0));
+        }
+        rc = launch_all(e, first_stream + c0, cn, n_samples, e->d_io_in.d + doff, e->d_io_out.d + doff, layout, cols);
+        if (rc) return rc;
+        if (piped) {
+            CUDA_TRY(cudaEventRecord(e->ev_done[c], e->stream));
+            CUDA_TRY(cudaStreamWaitEvent(s_out, e->ev_done[c], 0));
+        }
+        float* dst = layout == AIDAX_LAYOUT_PLANAR ? out + (size_t)c0 * stride : out + c0;
+        CUDA_TRY(cudaMemcpy2DAsync(dst, stride * sizeof(float), e->d_io_out.d + doff, cols * sizeof(float), cols * sizeof(float), rows,
+                                   cudaMemcpyDeviceToHost, s_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s_out));
+    if (piped) CUDA_TRY(cudaStreamSynchronize(e->stream));
     after_render(e, first_stream, n_streams, n_samples);
     return AIDAX_OK;
 }

@@ -7,6 +7,7 @@
 // renders that single stream synchronously (plain LV2 hosts) or, inside a batch opened through the
 // #batch extension (include/aidax_batch.h), defers to one launch for all instances.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -50,10 +51,14 @@ struct EngineHub {
     aidax_engine* engine = nullptr;
     int max_instances = 0, max_block = 0, device = -1;
     int refs = 0;
-    // batch state
-    bool batching = false;
+    // batch state: run() parks its ports in the slot of its own stream (no lock: every instance owns one
+    // slot, begin()/end() are called by the host while no run() is in flight), end() walks the slots in order
+    std::atomic<bool> batching{false};
     struct Pending { int stream; const float* in; float* out; uint32_t n; };
-    std::vector<Pending> pending;
+    struct Slot { const float* in; float* out; uint32_t n; uint32_t epoch; };
+    std::vector<Slot> slots;
+    uint32_t epoch = 0;
+    std::atomic<int> slot_hi{0}; // one past the highest stream id that parked in this batch
     float* stage_in = nullptr;  // pinned staging rows for scattered port buffers
     float* stage_out = nullptr;
 };
@@ -76,6 +81,8 @@ aidax_engine* hub_engine()
     if (aidax_engine_create(g_hub.device, g_hub.max_instances, g_hub.max_block, &g_hub.engine) != AIDAX_OK) {
         fprintf(stderr, "rt-neural-generic (aidax): cannot create the CUDA engine: %s\n", aidax_last_error());
         g_hub.engine = nullptr;
+    } else {
+        g_hub.slots.assign((size_t)g_hub.max_instances + 32, EngineHub::Slot{nullptr, nullptr, 0u, 0u});
     }
     return g_hub.engine;
 }
@@ -94,8 +101,9 @@ int batch_configure(int max_instances, int max_block, int device)
 int batch_begin()
 {
     std::lock_guard<std::mutex> lk(g_hub.mu);
-    g_hub.batching = true;
-    g_hub.pending.clear();
+    g_hub.epoch++;
+    g_hub.slot_hi.store(0, std::memory_order_relaxed);
+    g_hub.batching.store(true, std::memory_order_release);
     return 0;
 }
 
@@ -106,7 +114,7 @@ int render_pending(std::vector<EngineHub::Pending>& items)
 {
     aidax_engine* e = g_hub.engine;
     if (!e || items.empty()) return 0;
-    std::sort(items.begin(), items.end(), [](const EngineHub::Pending& a, const EngineHub::Pending& b) { return a.stream < b.stream; });
+    // items arrive sorted by stream id (batch_end walks the slot table in order)
     size_t i = 0;
     while (i < items.size()) {
         const EngineHub::Pending& a = items[i];
@@ -138,11 +146,16 @@ int render_pending(std::vector<EngineHub::Pending>& items)
 
 int batch_end()
 {
-    std::vector<EngineHub::Pending> items;
+    static std::vector<EngineHub::Pending> items; // reused across periods (the host calls end() from one thread)
+    items.clear();
     {
         std::lock_guard<std::mutex> lk(g_hub.mu);
-        g_hub.batching = false;
-        items.swap(g_hub.pending);
+        g_hub.batching.store(false, std::memory_order_release);
+        const int hi = std::min<int>(g_hub.slot_hi.load(std::memory_order_acquire), (int)g_hub.slots.size());
+        for (int s = 0; s < hi; ++s) {
+            const EngineHub::Slot& sl = g_hub.slots[s];
+            if (sl.epoch == g_hub.epoch) items.push_back(EngineHub::Pending{s, sl.in, sl.out, sl.n});
+        }
     }
     return render_pending(items);
 }
@@ -332,12 +345,11 @@ void run(LV2_Handle instance, uint32_t n_samples)
     if (!self->in || !self->out_1) return;
 
     bool deferred = false;
-    {
-        std::lock_guard<std::mutex> lk(g_hub.mu);
-        if (g_hub.batching) {
-            g_hub.pending.push_back(EngineHub::Pending{self->stream, self->in, self->out_1, n_samples});
-            deferred = true;
-        }
+    if (g_hub.batching.load(std::memory_order_acquire) && self->stream >= 0 && (size_t)self->stream < g_hub.slots.size()) {
+        g_hub.slots[self->stream] = EngineHub::Slot{self->in, self->out_1, n_samples, g_hub.epoch};
+        int hi = g_hub.slot_hi.load(std::memory_order_relaxed);
+        while (hi <= self->stream && !g_hub.slot_hi.compare_exchange_weak(hi, self->stream + 1, std::memory_order_release, std::memory_order_relaxed)) {}
+        deferred = true;
     }
     if (!deferred) {
         // lone instance: render this stream now and wait, so run() has LV2 semantics

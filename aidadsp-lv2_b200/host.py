@@ -29,6 +29,8 @@ def _load():
         L.aidax_host_is_batched.argtypes = [vp]
         L.aidax_host_launch_count.argtypes = [vp]
         L.aidax_host_launch_count.restype = C.c_uint64
+        L.aidax_host_timing.argtypes = [vp, C.POINTER(C.c_double)]
+        L.aidax_host_timing.restype = None
         L.aidax_host_input.argtypes = [vp]
         L.aidax_host_input.restype = vp
         L.aidax_host_output.argtypes = [vp]
@@ -103,6 +105,12 @@ class BatchHost:
         self.input[:, :n] = x
         self.run(n)
         return self.output[:, :n].copy()
+
+    def timing(self):
+        """(seconds in the N run() calls, seconds in batch end(), periods) since open()."""
+        out = (C.c_double * 3)()
+        self.lib.aidax_host_timing(self.h, out)
+        return float(out[0]), float(out[1]), float(out[2])
 
     def notify_count(self, instance=0):
         return int(self.lib.aidax_host_notify_count(self.h, instance))

@@ -36,6 +36,9 @@ void aidax_host_close(aidax_host* h);
 int aidax_host_n_instances(const aidax_host* h);
 int aidax_host_is_batched(const aidax_host* h);
 uint64_t aidax_host_launch_count(const aidax_host* h);
+/* Wall-clock seconds spent since open() in the two phases of aidax_host_run: out[0] = the N run() calls (control decode,
+ * atom handling, port parking), out[1] = the batch end() (copies + kernels + synchronise), out[2] = periods rendered. */
+void aidax_host_timing(const aidax_host* h, double out[3]);
 
 /* Audio arena: row i (stride aidax_host_stride() floats) is connected to instance i's IN / OUT port. */
 float* aidax_host_input(aidax_host* h);
