@@ -36,6 +36,8 @@ void set_err(const char* fmt, ...)
 }
 
 constexpr int kPortCount = 25;  // ttl/rt-neural-generic.ttl: ports 0..24
+constexpr int kFirstControl = 4;
+constexpr int kCtlPitch = 32;   // floats per instance in the control arena: ports 4..24 at the start of a 128-byte aligned row
 constexpr int kPortIn = 0, kPortOut = 1, kPortControl = 2, kPortNotify = 3;
 
 // ------------------------------------------------------------------ urid:map
@@ -171,7 +173,12 @@ struct aidax_host {
     float* in = nullptr;
     float* out = nullptr;
     bool arena_from_plugin = false;
-    std::vector<float> controls; // [n][kPortCount]
+    float* controls = nullptr;   // [n][kCtlPitch], 64-byte aligned; port p of instance i at i*kCtlPitch + p - kFirstControl
+    float* ctl(int i, int port) { return controls + (size_t)i * kCtlPitch + (port - kFirstControl); }
+    const float* ctl(int i, int port) const { return controls + (size_t)i * kCtlPitch + (port - kFirstControl); }
+    // what the per-period loop needs of an instance, packed (the full records below are touched on events only)
+    struct Hot { LV2_Handle handle; uint8_t* notify_buf; bool control_pending; };
+    std::vector<Hot> hot;
     std::vector<Instance> inst;
     std::vector<uint8_t> notify_storage;
     uint32_t notify_cap = 0;
@@ -234,6 +241,8 @@ void build_load_message(aidax_host* h, Instance& in, const char* path)
     lv2_atom_forge_pop(&forge, &obj_frame);
     lv2_atom_forge_pop(&forge, &seq_frame);
     in.control_pending = true;
+    const size_t idx = (size_t)(&in - h->inst.data());
+    if (idx < h->hot.size()) h->hot[idx].control_pending = true;
 }
 
 // count patch:Set notifications in an instance's NOTIFY buffer
@@ -255,18 +264,33 @@ void scan_notify(aidax_host* h, Instance& in)
 
 void run_instances(aidax_host* h, int lo, int hi, uint32_t n_samples)
 {
+    constexpr int kAhead = 4;
+    const uint32_t notify_room = h->notify_cap - (uint32_t)sizeof(LV2_Atom);
     for (int i = lo; i < hi; ++i) {
-        Instance& in = h->inst[i];
+        // run() of a small-state plugin is bound by cache misses on per-instance data that lives in several places
+        // (plugin object, control row, notify buffer): start fetching a few instances ahead
+        if (i + kAhead < h->n) {
+            const aidax_host::Hot& nx = h->hot[i + kAhead];
+            const char* ph = (const char*)nx.handle;
+            __builtin_prefetch(ph);
+            __builtin_prefetch(ph + 64);
+            __builtin_prefetch(ph + 128);
+            __builtin_prefetch(nx.notify_buf, 1);
+            __builtin_prefetch(h->ctl(i + kAhead, kFirstControl), 1);
+            __builtin_prefetch(h->ctl(i + kAhead, kFirstControl + 16));
+        }
+        aidax_host::Hot& hot = h->hot[i];
         // an LV2 host presents an output atom port as an empty chunk whose size is the capacity
-        LV2_Atom_Sequence* ns = (LV2_Atom_Sequence*)in.notify_buf;
-        ns->atom.size = h->notify_cap - (uint32_t)sizeof(LV2_Atom);
+        LV2_Atom_Sequence* ns = (LV2_Atom_Sequence*)hot.notify_buf;
+        ns->atom.size = notify_room;
         ns->atom.type = 0;
-        if (in.control_pending) h->desc->connect_port(in.handle, kPortControl, in.control_buf.data());
-        h->desc->run(in.handle, n_samples);
-        if (in.control_pending) {
-            h->desc->connect_port(in.handle, kPortControl, h->empty_seq);
-            in.control_pending = false;
-            in.control_buf.clear();
+        if (hot.control_pending) h->desc->connect_port(hot.handle, kPortControl, h->inst[i].control_buf.data());
+        h->desc->run(hot.handle, n_samples);
+        if (hot.control_pending) {
+            h->desc->connect_port(hot.handle, kPortControl, h->empty_seq);
+            hot.control_pending = false;
+            h->inst[i].control_pending = false;
+            h->inst[i].control_buf.clear();
         }
     }
 }
@@ -370,10 +394,11 @@ aidax_host* aidax_host_open(const char* plugin_so, double sample_rate, int n_ins
     memset(h->out, 0, arena_bytes);
 
     // ttl defaults (ttl/rt-neural-generic.ttl:92-313)
-    h->controls.assign((size_t)n_instances * kPortCount, 0.f);
+    if (posix_memalign((void**)&h->controls, 64, (size_t)n_instances * kCtlPitch * sizeof(float)) != 0) { set_err("control arena allocation failed"); return nullptr; }
+    memset(h->controls, 0, (size_t)n_instances * kCtlPitch * sizeof(float));
     for (int i = 0; i < n_instances; ++i) {
-        float* c = &h->controls[(size_t)i * kPortCount];
-        c[4] = 66.216f; c[12] = 305.f; c[14] = 750.f; c[15] = 0.707f; c[18] = 2000.f; c[21] = 1.f; c[24] = 1.f;
+        *h->ctl(i, 4) = 66.216f; *h->ctl(i, 12) = 305.f; *h->ctl(i, 14) = 750.f; *h->ctl(i, 15) = 0.707f;
+        *h->ctl(i, 18) = 2000.f; *h->ctl(i, 21) = 1.f; *h->ctl(i, 24) = 1.f;
     }
     h->notify_cap = n_instances <= 8192 ? 2048u : 384u;
     h->notify_storage.assign((size_t)n_instances * h->notify_cap, 0);
@@ -398,8 +423,10 @@ aidax_host* aidax_host_open(const char* plugin_so, double sample_rate, int n_ins
         h->desc->connect_port(in.handle, kPortOut, h->out + (size_t)i * h->stride);
         h->desc->connect_port(in.handle, kPortControl, h->empty_seq);
         h->desc->connect_port(in.handle, kPortNotify, in.notify_buf);
-        for (int p = 4; p < kPortCount; ++p) h->desc->connect_port(in.handle, p, &h->controls[(size_t)i * kPortCount + p]);
+        for (int p = kFirstControl; p < kPortCount; ++p) h->desc->connect_port(in.handle, p, h->ctl(i, p));
     }
+    h->hot.resize(n_instances);
+    for (int i = 0; i < n_instances; ++i) h->hot[i] = aidax_host::Hot{h->inst[i].handle, h->inst[i].notify_buf, false};
     h->pool.reset(new Pool(n_threads));
     return h.release();
 }
@@ -415,6 +442,7 @@ void aidax_host_close(aidax_host* h)
         }
     if (h->arena_from_plugin) { h->batch->arena_free(h->in); h->batch->arena_free(h->out); }
     else { free(h->in); free(h->out); }
+    free(h->controls);
     // the plugin binary stays loaded: it may own process-wide state (CUDA context, engine)
     delete h;
 }
@@ -434,15 +462,15 @@ size_t aidax_host_stride(const aidax_host* h) { return h ? h->stride : 0; }
 int aidax_host_set_control(aidax_host* h, int instance, int port, float value)
 {
     if (!h || port < 4 || port >= kPortCount || instance >= h->n) { set_err("bad control address"); return 1; }
-    if (instance >= 0) h->controls[(size_t)instance * kPortCount + port] = value;
-    else for (int i = 0; i < h->n; ++i) h->controls[(size_t)i * kPortCount + port] = value;
+    if (instance >= 0) *h->ctl(instance, port) = value;
+    else for (int i = 0; i < h->n; ++i) *h->ctl(i, port) = value;
     return 0;
 }
 
 float aidax_host_get_control(const aidax_host* h, int instance, int port)
 {
     if (!h || port < 4 || port >= kPortCount || instance < 0 || instance >= h->n) return 0.f;
-    return h->controls[(size_t)instance * kPortCount + port];
+    return *h->ctl(instance, port);
 }
 
 int aidax_host_load_model(aidax_host* h, int instance, const char* json_path)
@@ -474,9 +502,17 @@ int aidax_host_run(aidax_host* h, int n_samples)
     int rc = 0;
     const auto t0 = std::chrono::steady_clock::now();
     if (h->batch) h->batch->begin();
-    h->pool->run([&](int w) {
-        const int lo = (int)((int64_t)n * w / nt), hi = (int)((int64_t)n * (w + 1) / nt);
-        run_instances(h, lo, hi, (uint32_t)n_samples);
+    // Instances are handed out in ascending blocks, so all threads work on the same neighbourhood of the arena and the
+    // plugin's batch extension sees its chunks complete one after another (it ships a chunk to the GPU as soon as the
+    // last instance of the chunk has run); it also balances threads when run() itself computes (the reference).
+    std::atomic<int> next{0};
+    const int grain = n >= 64 * nt ? 64 : std::max(1, n / (4 * nt));
+    h->pool->run([&](int) {
+        for (;;) {
+            const int lo = next.fetch_add(grain, std::memory_order_relaxed);
+            if (lo >= n) break;
+            run_instances(h, lo, std::min(n, lo + grain), (uint32_t)n_samples);
+        }
     });
     const auto t1 = std::chrono::steady_clock::now();
     if (h->batch) {

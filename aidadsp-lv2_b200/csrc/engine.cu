@@ -129,9 +129,18 @@ struct aidax_engine {
     uint64_t membership_epoch = 1;
     std::map<std::pair<int, int>, RangePlan> plans; // keyed by (first, n); the pipelined host path renders in chunks
     std::vector<const void*> attr_done;
-    // pipelined host rendering: copy-in / copy-out streams and per-chunk events
+    // pipelined host rendering: copy-in / copy-out streams, a few kernel streams (so that the kernels of
+    // small ranges share the GPU) and per-range events; `pending` = ranges submitted since the last wait
+    static constexpr int kMaxKernelStreams = 8;
     cudaStream_t stream_in = nullptr, stream_out = nullptr;
-    std::vector<cudaEvent_t> ev_in, ev_done;
+    cudaStream_t kstream[kMaxKernelStreams] = {};
+    int n_kstreams = 4;
+    cudaEvent_t ev_fork = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_done, ev_out;
+    bool trace = false;      // AIDAX_TRACE=1: per-range timeline of the host-fed pipeline on stderr
+    int trace_left = 3;
+    struct PendingRange { int first, n, n_samples; };
+    std::vector<PendingRange> pending;
 
     StreamArrays sa() const
     {
@@ -209,15 +218,15 @@ static void sync_stream_shadow(aidax_engine* e, int s)
 
 // upload [lo, hi) of a per-stream array with `rows` rows of pitch cap
 template <typename T>
-static cudaError_t upload_rows(aidax_engine* e, T* dev, const T* host, int rows, int lo, int hi)
+static cudaError_t upload_rows(aidax_engine* e, cudaStream_t st, T* dev, const T* host, int rows, int lo, int hi)
 {
     if (hi <= lo) return cudaSuccess;
-    if (rows == 1) return cudaMemcpyAsync(dev + lo, host + lo, (size_t)(hi - lo) * sizeof(T), cudaMemcpyHostToDevice, e->stream);
+    if (rows == 1) return cudaMemcpyAsync(dev + lo, host + lo, (size_t)(hi - lo) * sizeof(T), cudaMemcpyHostToDevice, st);
     return cudaMemcpy2DAsync(dev + lo, (size_t)e->cap * sizeof(T), host + lo, (size_t)e->cap * sizeof(T), (size_t)(hi - lo) * sizeof(T),
-                             rows, cudaMemcpyHostToDevice, e->stream);
+                             rows, cudaMemcpyHostToDevice, st);
 }
 
-static int upload_dirty(aidax_engine* e, int first, int n)
+static int upload_dirty(aidax_engine* e, int first, int n, cudaStream_t st)
 {
     if (e->models_dirty) {
         std::vector<ModelDev> md(e->models.size());
@@ -246,22 +255,22 @@ static int upload_dirty(aidax_engine* e, int first, int n)
             if ((s < first || s >= last) && (e->dirty_ctrl[s] || e->dirty_coef[s] || e->dirty_cmd[s])) remaining = true;
     }
     e->any_dirty = remaining;
-    CUDA_TRY(upload_rows(e, e->d_flags.d, e->h_flags.data(), 1, clo, chi));
-    CUDA_TRY(upload_rows(e, e->d_pre_target.d, e->h_pre_target.data(), 1, clo, chi));
-    CUDA_TRY(upload_rows(e, e->d_master_target.d, e->h_master_target.data(), 1, clo, chi));
-    CUDA_TRY(upload_rows(e, e->d_p_port.d, e->h_p_port.data(), 2, clo, chi));
-    CUDA_TRY(upload_rows(e, e->d_bq_coef.d, e->h_bq_coef.data(), kNumBiquads * 5, flo, fhi));
+    CUDA_TRY(upload_rows(e, st, e->d_flags.d, e->h_flags.data(), 1, clo, chi));
+    CUDA_TRY(upload_rows(e, st, e->d_pre_target.d, e->h_pre_target.data(), 1, clo, chi));
+    CUDA_TRY(upload_rows(e, st, e->d_master_target.d, e->h_master_target.data(), 1, clo, chi));
+    CUDA_TRY(upload_rows(e, st, e->d_p_port.d, e->h_p_port.data(), 2, clo, chi));
+    CUDA_TRY(upload_rows(e, st, e->d_bq_coef.d, e->h_bq_coef.data(), kNumBiquads * 5, flo, fhi));
     if (mhi > mlo) {
         // Commands for streams outside [mlo, mhi) of this upload keep their device copy: the device
         // clears a command when it executes it, and the host clears its shadow after uploading it.
-        CUDA_TRY(upload_rows(e, e->d_cmd.d, e->h_cmd.data(), 1, mlo, mhi));
-        CUDA_TRY(upload_rows(e, e->d_p_init.d, e->h_p_init.data(), 2, mlo, mhi));
-        CUDA_TRY(upload_rows(e, e->d_cmd_pre_mem.d, e->h_cmd_pre_mem.data(), 1, mlo, mhi));
-        CUDA_TRY(upload_rows(e, e->d_cmd_master_mem.d, e->h_cmd_master_mem.data(), 1, mlo, mhi));
-        CUDA_TRY(upload_rows(e, e->d_exp_coef.d, e->h_exp_coef.data(), 1, mlo, mhi));
-        CUDA_TRY(upload_rows(e, e->d_lin_denom.d, e->h_lin_denom.data(), 1, mlo, mhi));
+        CUDA_TRY(upload_rows(e, st, e->d_cmd.d, e->h_cmd.data(), 1, mlo, mhi));
+        CUDA_TRY(upload_rows(e, st, e->d_p_init.d, e->h_p_init.data(), 2, mlo, mhi));
+        CUDA_TRY(upload_rows(e, st, e->d_cmd_pre_mem.d, e->h_cmd_pre_mem.data(), 1, mlo, mhi));
+        CUDA_TRY(upload_rows(e, st, e->d_cmd_master_mem.d, e->h_cmd_master_mem.data(), 1, mlo, mhi));
+        CUDA_TRY(upload_rows(e, st, e->d_exp_coef.d, e->h_exp_coef.data(), 1, mlo, mhi));
+        CUDA_TRY(upload_rows(e, st, e->d_lin_denom.d, e->h_lin_denom.data(), 1, mlo, mhi));
         // pageable host memory: the async copies above are staged before returning, so the shadow can be cleared
-        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        CUDA_TRY(cudaStreamSynchronize(st));
         for (int s = mlo; s < mhi; ++s) e->h_cmd[s] = 0;
     }
     return AIDAX_OK;
@@ -282,10 +291,19 @@ static const KernelVariant* choose_variant(const aidax_engine* e, const Family& 
     return v.front();
 }
 
+// every stream a render kernel may be running on (block tables are replaced only when all of them are idle)
+static cudaError_t sync_kernel_streams(aidax_engine* e)
+{
+    cudaError_t err = cudaStreamSynchronize(e->stream);
+    for (int k = 0; k < e->n_kstreams && err == cudaSuccess; ++k)
+        if (e->kstream[k] != e->stream) err = cudaStreamSynchronize(e->kstream[k]);
+    return err;
+}
+
 static int build_plan(aidax_engine* e, int first, int n, RangePlan** out)
 {
     if (e->plans.size() > 256) { // ranges come and go (chunk sizes change): drop stale tables
-        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        CUDA_TRY(sync_kernel_streams(e));
         for (auto& kv : e->plans) kv.second.d_tables.release();
         e->plans.clear();
     }
@@ -330,12 +348,12 @@ static int build_plan(aidax_engine* e, int first, int n, RangePlan** out)
         rp.launches.push_back(lp);
     }
     if (rp.d_tables.n < e->h_tables.size()) {
-        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        CUDA_TRY(sync_kernel_streams(e));
         rp.d_tables.release();
         CUDA_TRY(rp.d_tables.alloc(e->h_tables.size() * 2 + 1024));
     }
     if (!e->h_tables.empty()) {
-        CUDA_TRY(cudaStreamSynchronize(e->stream)); // a previous launch may still read the old table
+        CUDA_TRY(sync_kernel_streams(e)); // a previous launch may still read the old table
         CUDA_TRY(cudaMemcpy(rp.d_tables.d, e->h_tables.data(), e->h_tables.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
     rp.epoch = e->membership_epoch;
@@ -343,9 +361,9 @@ static int build_plan(aidax_engine* e, int first, int n, RangePlan** out)
     return AIDAX_OK;
 }
 
-static int launch_all(aidax_engine* e, int first, int n, int n_samples, const float* d_in, float* d_out, int layout, size_t stride)
+static int launch_all(aidax_engine* e, cudaStream_t st, int first, int n, int n_samples, const float* d_in, float* d_out, int layout, size_t stride)
 {
-    int rc = upload_dirty(e, first, n);
+    int rc = upload_dirty(e, first, n, st);
     if (rc) return rc;
     RangePlan* rp = nullptr;
     rc = build_plan(e, first, n, &rp);
@@ -372,7 +390,7 @@ static int launch_all(aidax_engine* e, int first, int n, int n_samples, const fl
         p.models = e->d_models.d;
         p.sa = e->sa();
         void* args[] = {&p};
-        CUDA_TRY(cudaLaunchKernel(fn, dim3(lp.n_blocks), dim3(kv->NW * 32), args, smem, e->stream));
+        CUDA_TRY(cudaLaunchKernel(fn, dim3(lp.n_blocks), dim3(kv->NW * 32), args, smem, st));
         e->launches++;
     }
     return AIDAX_OK;
@@ -433,6 +451,11 @@ int aidax_engine_create(int device, int max_streams, int max_block, aidax_engine
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_out, cudaStreamNonBlocking));
+    if (const char* v = std::getenv("AIDAX_KERNEL_STREAMS")) e->n_kstreams = std::max(1, std::min(std::atoi(v), (int)aidax_engine::kMaxKernelStreams));
+    e->kstream[0] = e->stream;
+    for (int k = 1; k < e->n_kstreams; ++k) CUDA_TRY(cudaStreamCreateWithFlags(&e->kstream[k], cudaStreamNonBlocking));
+    e->trace = std::getenv("AIDAX_TRACE") != nullptr;
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, e->trace ? cudaEventDefault : cudaEventDisableTiming));
     const size_t cap = (size_t)e->cap;
     e->streams.resize(cap);
     e->dirty_ctrl.assign(cap, 0); e->dirty_coef.assign(cap, 0); e->dirty_cmd.assign(cap, 0);
@@ -462,7 +485,7 @@ int aidax_engine_destroy(aidax_engine* e)
 {
     if (!e) return AIDAX_OK;
     cudaSetDevice(e->device);
-    cudaStreamSynchronize(e->stream);
+    cudaDeviceSynchronize();
     for (ModelEntry& m : e->models) if (m.d_weights) cudaFree(m.d_weights);
     e->d_flags.release(); e->d_cmd.release(); e->d_dflags.release(); e->d_pre_target.release(); e->d_master_target.release();
     e->d_p_port.release(); e->d_p_init.release(); e->d_cmd_pre_mem.release(); e->d_cmd_master_mem.release();
@@ -473,6 +496,9 @@ int aidax_engine_destroy(aidax_engine* e)
     for (auto& kv : e->plans) kv.second.d_tables.release();
     for (cudaEvent_t ev : e->ev_in) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->ev_done) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->ev_out) cudaEventDestroy(ev);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    for (int k = 1; k < e->n_kstreams; ++k) if (e->kstream[k]) cudaStreamDestroy(e->kstream[k]);
     if (e->stream_in) cudaStreamDestroy(e->stream_in);
     if (e->stream_out) cudaStreamDestroy(e->stream_out);
     cudaStreamDestroy(e->stream);
@@ -795,65 +821,142 @@ int aidax_render_device(aidax_engine* e, int first_stream, int n_streams, int n_
     if (n_samples == 0 || n_streams == 0) return AIDAX_OK; // run() with 0 samples is a legal no-op for audio (:606-609)
     std::lock_guard<std::mutex> lk(e->mu);
     CUDA_TRY(cudaSetDevice(e->device));
-    rc = launch_all(e, first_stream, n_streams, n_samples, d_in, d_out, layout, stride);
+    rc = launch_all(e, e->stream, first_stream, n_streams, n_samples, d_in, d_out, layout, stride);
     if (rc) return rc;
     after_render(e, first_stream, n_streams, n_samples);
+    return AIDAX_OK;
+}
+
+// One stream range through the copy-in stream, a kernel stream and the copy-out stream; returns without waiting.
+// (`serial`: a small lone range runs copy, kernel and copy back to back on the engine stream -- no cross-stream events.)
+static int submit_range(aidax_engine* e, int first_stream, int n_streams, int n_samples, const float* in, float* out, int layout, size_t stride,
+                        bool serial = false)
+{
+    const size_t idx = e->pending.size();
+    while (e->ev_in.size() <= idx) {
+        cudaEvent_t a, b, c;
+        const unsigned fl = e->trace ? cudaEventDefault : cudaEventDisableTiming;
+        CUDA_TRY(cudaEventCreateWithFlags(&a, fl));
+        CUDA_TRY(cudaEventCreateWithFlags(&b, fl));
+        CUDA_TRY(cudaEventCreateWithFlags(&c, fl));
+        e->ev_in.push_back(a);
+        e->ev_done.push_back(b);
+        e->ev_out.push_back(c);
+    }
+    cudaStream_t ks = serial ? e->stream : e->kstream[idx % (size_t)e->n_kstreams];
+    cudaStream_t s_in = serial ? e->stream : e->stream_in, s_out = serial ? e->stream : e->stream_out;
+    if (idx == 0 && !serial) {
+        // work enqueued on the engine stream by aidax_render_device stays ordered before this period
+        CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));
+        for (int k = 0; k < e->n_kstreams; ++k)
+            if (e->kstream[k] != e->stream) CUDA_TRY(cudaStreamWaitEvent(e->kstream[k], e->ev_fork, 0));
+    }
+    const size_t rows = layout == AIDAX_LAYOUT_PLANAR ? (size_t)n_streams : (size_t)n_samples;
+    const size_t cols = layout == AIDAX_LAYOUT_PLANAR ? (size_t)n_samples : (size_t)n_streams;
+    const size_t doff = (size_t)first_stream * (size_t)e->max_block; // every stream owns max_block samples of the device arena
+    if (stride == cols) {
+        CUDA_TRY(cudaMemcpyAsync(e->d_io_in.d + doff, in, rows * cols * sizeof(float), cudaMemcpyHostToDevice, s_in));
+    } else {
+        CUDA_TRY(cudaMemcpy2DAsync(e->d_io_in.d + doff, cols * sizeof(float), in, stride * sizeof(float), cols * sizeof(float), rows,
+                                   cudaMemcpyHostToDevice, s_in));
+    }
+    if (!serial) {
+        CUDA_TRY(cudaEventRecord(e->ev_in[idx], s_in));
+        CUDA_TRY(cudaStreamWaitEvent(ks, e->ev_in[idx], 0));
+    }
+    const int rc = launch_all(e, ks, first_stream, n_streams, n_samples, e->d_io_in.d + doff, e->d_io_out.d + doff, layout, cols);
+    if (rc) return rc;
+    if (!serial) {
+        CUDA_TRY(cudaEventRecord(e->ev_done[idx], ks));
+        CUDA_TRY(cudaStreamWaitEvent(s_out, e->ev_done[idx], 0));
+    }
+    if (stride == cols) {
+        CUDA_TRY(cudaMemcpyAsync(out, e->d_io_out.d + doff, rows * cols * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+    } else {
+        CUDA_TRY(cudaMemcpy2DAsync(out, stride * sizeof(float), e->d_io_out.d + doff, cols * sizeof(float), cols * sizeof(float), rows,
+                                   cudaMemcpyDeviceToHost, s_out));
+    }
+    if (e->trace && !serial) CUDA_TRY(cudaEventRecord(e->ev_out[idx], s_out));
+    e->pending.push_back(aidax_engine::PendingRange{first_stream, n_streams, n_samples});
+    return AIDAX_OK;
+}
+
+static int wait_ranges(aidax_engine* e)
+{
+    if (e->pending.empty()) return AIDAX_OK;
+    // every D2H copy is on stream_out and waits for its kernel, so this covers the kernel streams too;
+    // the engine stream is re-joined so that later aidax_render_device calls stay ordered after this period
+    cudaError_t err = sync_kernel_streams(e);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream_out);
+    if (e->trace && err == cudaSuccess && e->pending.size() > 1 && e->trace_left > 0) {
+        --e->trace_left;
+        fprintf(stderr, "aidax trace: %zu ranges (ms after the first submit: copy-in done, kernels done, copy-out done)\n", e->pending.size());
+        for (size_t i = 0; i < e->pending.size(); ++i) {
+            float a = 0.f, b = 0.f, c = 0.f;
+            cudaEventElapsedTime(&a, e->ev_fork, e->ev_in[i]);
+            cudaEventElapsedTime(&b, e->ev_fork, e->ev_done[i]);
+            cudaEventElapsedTime(&c, e->ev_fork, e->ev_out[i]);
+            fprintf(stderr, "  range %2zu [%7d +%6d]  in %7.3f  kernel %7.3f  out %7.3f\n", i, e->pending[i].first, e->pending[i].n, a, b, c);
+        }
+    }
+    for (const aidax_engine::PendingRange& r : e->pending) after_render(e, r.first, r.n, r.n_samples);
+    e->pending.clear();
+    CUDA_TRY(err);
+    return AIDAX_OK;
+}
+
+static int render_host_checks(aidax_engine* e, int first_stream, int n_streams, int n_samples, const float* in, float* out, int layout, size_t stride)
+{
+    int rc = render_common_checks(e, first_stream, n_streams, n_samples, in, out, layout);
+    if (rc) return rc;
+    // Staged through the engine's device arena with a dense pitch (planar: n_samples, interleaved: n_streams)
+    if (layout == AIDAX_LAYOUT_PLANAR ? stride < (size_t)n_samples : stride < (size_t)n_streams)
+        return fail(AIDAX_ERR_ARG, "stride %zu smaller than a row", stride);
     return AIDAX_OK;
 }
 
 int aidax_render_host(aidax_engine* e, int first_stream, int n_streams, int n_samples, const float* in, float* out,
                       int layout, size_t stride)
 {
-    int rc = render_common_checks(e, first_stream, n_streams, n_samples, in, out, layout);
+    int rc = render_host_checks(e, first_stream, n_streams, n_samples, in, out, layout, stride);
     if (rc) return rc;
     if (n_samples == 0 || n_streams == 0) return AIDAX_OK;
     std::lock_guard<std::mutex> lk(e->mu);
     CUDA_TRY(cudaSetDevice(e->device));
-    // Stage through the engine's device arena with a dense pitch (planar: n_samples, interleaved: n_streams)
-    if (layout == AIDAX_LAYOUT_PLANAR ? stride < (size_t)n_samples : stride < (size_t)n_streams)
-        return fail(AIDAX_ERR_ARG, "stride %zu smaller than a row", stride);
-    // Large periods are cut into stream chunks that flow through three CUDA streams (copy in -> kernels -> copy
-    // out), so that on a PCIe-attached GPU the two copy directions and the kernels overlap; a small period is one chunk.
+    // Large periods are cut into stream chunks that flow through the copy-in, kernel and copy-out streams, so that on a
+    // PCIe-attached GPU the two copy directions and the kernels overlap; a small period is one chunk.
     const size_t bytes = (size_t)n_streams * (size_t)n_samples * sizeof(float);
     int n_chunks = (int)std::min<size_t>(8, std::max<size_t>(1, bytes / ((size_t)8 << 20)));
     int chunk = (n_streams + n_chunks - 1) / n_chunks;
     chunk = (chunk + 1023) & ~1023; // whole tiles of every kernel shape
     n_chunks = (n_streams + chunk - 1) / chunk;
-    while ((int)e->ev_in.size() < n_chunks) {
-        cudaEvent_t a, b;
-        CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
-        e->ev_in.push_back(a);
-        e->ev_done.push_back(b);
-    }
-    const bool piped = n_chunks > 1;
-    cudaStream_t s_in = piped ? e->stream_in : e->stream, s_out = piped ? e->stream_out : e->stream;
-    for (int c = 0; c < n_chunks; ++c) {
+    const bool serial = n_chunks == 1 && e->pending.empty();
+    for (int c = 0; c < n_chunks && rc == AIDAX_OK; ++c) {
         const int c0 = c * chunk, cn = std::min(chunk, n_streams - c0);
-        const size_t rows = layout == AIDAX_LAYOUT_PLANAR ? (size_t)cn : (size_t)n_samples;
-        const size_t cols = layout == AIDAX_LAYOUT_PLANAR ? (size_t)n_samples : (size_t)cn;
-        const size_t doff = (size_t)c0 * (size_t)n_samples; // chunks are dense, back to back in the arena
-        const float* src = layout == AIDAX_LAYOUT_PLANAR ? in + (size_t)c0 * stride : in + c0;
-        CUDA_TRY(cudaMemcpy2DAsync(e->d_io_in.d + doff, cols * sizeof(float), src, stride * sizeof(float), cols * sizeof(float), rows,
-                                   cudaMemcpyHostToDevice, s_in));
-        if (piped) {
-            CUDA_TRY(cudaEventRecord(e->ev_in[c], s_in));
-            CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_in[c], 0));
-        }
-        rc = launch_all(e, first_stream + c0, cn, n_samples, e->d_io_in.d + doff, e->d_io_out.d + doff, layout, cols);
-        if (rc) return rc;
-        if (piped) {
-            CUDA_TRY(cudaEventRecord(e->ev_done[c], e->stream));
-            CUDA_TRY(cudaStreamWaitEvent(s_out, e->ev_done[c], 0));
-        }
-        float* dst = layout == AIDAX_LAYOUT_PLANAR ? out + (size_t)c0 * stride : out + c0;
-        CUDA_TRY(cudaMemcpy2DAsync(dst, stride * sizeof(float), e->d_io_out.d + doff, cols * sizeof(float), cols * sizeof(float), rows,
-                                   cudaMemcpyDeviceToHost, s_out));
+        const size_t hoff = layout == AIDAX_LAYOUT_PLANAR ? (size_t)c0 * stride : (size_t)c0; // rows resp. columns of the caller's block
+        rc = submit_range(e, first_stream + c0, cn, n_samples, in + hoff, out + hoff, layout, stride, serial);
     }
-    CUDA_TRY(cudaStreamSynchronize(s_out));
-    if (piped) CUDA_TRY(cudaStreamSynchronize(e->stream));
-    after_render(e, first_stream, n_streams, n_samples);
-    return AIDAX_OK;
+    const int rc_wait = wait_ranges(e);
+    return rc ? rc : rc_wait;
+}
+
+int aidax_render_host_submit(aidax_engine* e, int first_stream, int n_streams, int n_samples, const float* in, float* out,
+                             int layout, size_t stride)
+{
+    int rc = render_host_checks(e, first_stream, n_streams, n_samples, in, out, layout, stride);
+    if (rc) return rc;
+    if (n_samples == 0 || n_streams == 0) return AIDAX_OK;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    return submit_range(e, first_stream, n_streams, n_samples, in, out, layout, stride);
+}
+
+int aidax_render_host_wait(aidax_engine* e)
+{
+    if (!e) return fail(AIDAX_ERR_ARG, "null engine");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    return wait_ranges(e);
 }
 
 int aidax_engine_synchronize(aidax_engine* e)
@@ -906,6 +1009,69 @@ int aidax_measure_fp32_peak(int device, int millis, double* tflops_out)
     cudaFree(d);
     *tflops_out = best;
     return AIDAX_OK;
+}
+
+int aidax_measure_pcie(int device, size_t bytes, double gbs_out[3])
+{
+    if (!gbs_out || bytes < ((size_t)1 << 20)) return fail(AIDAX_ERR_ARG, "bad measure_pcie arguments");
+    CUDA_TRY(cudaSetDevice(device));
+    float *h_a = nullptr, *h_b = nullptr, *d_a = nullptr, *d_b = nullptr;
+    cudaStream_t s0 = nullptr, s1 = nullptr;
+    cudaEvent_t a = nullptr, b = nullptr, c = nullptr;
+    int rc = AIDAX_OK;
+    auto body = [&]() -> int {
+        CUDA_TRY(cudaHostAlloc((void**)&h_a, bytes, cudaHostAllocDefault));
+        CUDA_TRY(cudaHostAlloc((void**)&h_b, bytes, cudaHostAllocDefault));
+        CUDA_TRY(cudaMalloc((void**)&d_a, bytes));
+        CUDA_TRY(cudaMalloc((void**)&d_b, bytes));
+        std::memset(h_a, 0, bytes);
+        std::memset(h_b, 0, bytes);
+        CUDA_TRY(cudaStreamCreateWithFlags(&s0, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&a));
+        CUDA_TRY(cudaEventCreate(&b));
+        CUDA_TRY(cudaEventCreate(&c));
+        double best[3] = {0.0, 0.0, 0.0};
+        for (int it = 0; it < 4; ++it) {
+            float ms = 0.f;
+            CUDA_TRY(cudaEventRecord(a, s0));
+            CUDA_TRY(cudaMemcpyAsync(d_a, h_a, bytes, cudaMemcpyHostToDevice, s0));
+            CUDA_TRY(cudaEventRecord(b, s0));
+            CUDA_TRY(cudaEventSynchronize(b));
+            CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+            best[0] = std::max(best[0], (double)bytes / (ms * 1e-3) / 1e9);
+            CUDA_TRY(cudaEventRecord(a, s0));
+            CUDA_TRY(cudaMemcpyAsync(h_b, d_b, bytes, cudaMemcpyDeviceToHost, s0));
+            CUDA_TRY(cudaEventRecord(b, s0));
+            CUDA_TRY(cudaEventSynchronize(b));
+            CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+            best[1] = std::max(best[1], (double)bytes / (ms * 1e-3) / 1e9);
+            // both directions at once: the slower direction's rate while the other one is busy
+            CUDA_TRY(cudaEventRecord(a, s0));
+            CUDA_TRY(cudaStreamWaitEvent(s1, a, 0));
+            CUDA_TRY(cudaMemcpyAsync(d_a, h_a, bytes, cudaMemcpyHostToDevice, s0));
+            CUDA_TRY(cudaMemcpyAsync(h_b, d_b, bytes, cudaMemcpyDeviceToHost, s1));
+            CUDA_TRY(cudaEventRecord(c, s1));
+            CUDA_TRY(cudaStreamWaitEvent(s0, c, 0));
+            CUDA_TRY(cudaEventRecord(b, s0));
+            CUDA_TRY(cudaEventSynchronize(b));
+            CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+            best[2] = std::max(best[2], (double)bytes / (ms * 1e-3) / 1e9);
+        }
+        for (int i = 0; i < 3; ++i) gbs_out[i] = best[i];
+        return AIDAX_OK;
+    };
+    rc = body();
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+    if (c) cudaEventDestroy(c);
+    if (s0) cudaStreamDestroy(s0);
+    if (s1) cudaStreamDestroy(s1);
+    if (d_a) cudaFree(d_a);
+    if (d_b) cudaFree(d_b);
+    if (h_a) cudaFreeHost(h_a);
+    if (h_b) cudaFreeHost(h_b);
+    return rc;
 }
 
 uint64_t aidax_engine_launch_count(aidax_engine* e) { return e ? e->launches : 0; }

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -58,9 +59,27 @@ struct EngineHub {
     struct Slot { const float* in; float* out; uint32_t n; uint32_t epoch; };
     std::vector<Slot> slots;
     uint32_t epoch = 0;
-    std::atomic<int> slot_hi{0}; // one past the highest stream id that parked in this batch
-    float* stage_in = nullptr;  // pinned staging rows for scattered port buffers
-    float* stage_out = nullptr;
+    // Streaming hand-over: stream ids are cut into fixed chunks; the run() that parks the last live instance of a
+    // chunk submits that chunk's copy-in / kernels / copy-out at once (aidax_render_host_submit), so the transfers
+    // of early chunks overlap the run() calls of later ones.  end() renders what is left and waits.
+    // Counting is two-level so that run() calls on different host threads do not fight over one cache line: a run()
+    // bumps the counter of its 64-stream block (a host thread works through neighbouring instances, so a block's
+    // line stays in its cache); the run() that fills a block bumps the chunk's counter.
+    static constexpr int kBlockStreams = 64;
+    int chunk_streams = 16384;
+    struct alignas(64) Block {
+        std::atomic<int> parked{0};   // instances of this block that ran in the current batch
+        std::atomic<int> live{0};     // instances whose stream id lies in this block
+    };
+    struct alignas(64) Chunk {
+        std::atomic<int> blocks_done{0};  // blocks of this chunk whose live instances have all run in the current batch
+        std::atomic<int> blocks_live{0};  // blocks with at least one live instance
+        std::atomic<uint32_t> submitted_epoch{0};
+    };
+    std::unique_ptr<Block[]> blocks;
+    std::unique_ptr<Chunk[]> chunks;
+    int n_blocks = 0, n_chunks = 0;
+    std::atomic<int> submit_error{0};
 };
 EngineHub g_hub;
 
@@ -83,6 +102,11 @@ aidax_engine* hub_engine()
         g_hub.engine = nullptr;
     } else {
         g_hub.slots.assign((size_t)g_hub.max_instances + 32, EngineHub::Slot{nullptr, nullptr, 0u, 0u});
+        g_hub.chunk_streams = std::max(128, env_int("AIDAX_BATCH_CHUNK", 16384)) & ~127; // whole tiles of every kernel shape
+        g_hub.n_chunks = (int)((g_hub.slots.size() + g_hub.chunk_streams - 1) / g_hub.chunk_streams);
+        g_hub.n_blocks = g_hub.n_chunks * (g_hub.chunk_streams / EngineHub::kBlockStreams);
+        g_hub.chunks.reset(new EngineHub::Chunk[g_hub.n_chunks]);
+        g_hub.blocks.reset(new EngineHub::Block[g_hub.n_blocks]);
     }
     return g_hub.engine;
 }
@@ -102,7 +126,9 @@ int batch_begin()
 {
     std::lock_guard<std::mutex> lk(g_hub.mu);
     g_hub.epoch++;
-    g_hub.slot_hi.store(0, std::memory_order_relaxed);
+    g_hub.submit_error.store(0, std::memory_order_relaxed);
+    for (int c = 0; c < g_hub.n_chunks; ++c) g_hub.chunks[c].blocks_done.store(0, std::memory_order_relaxed);
+    for (int b = 0; b < g_hub.n_blocks; ++b) g_hub.blocks[b].parked.store(0, std::memory_order_relaxed);
     g_hub.batching.store(true, std::memory_order_release);
     return 0;
 }
@@ -134,7 +160,7 @@ int render_pending(std::vector<EngineHub::Pending>& items)
         const int count = (int)(j - i);
         int rc;
         if (count > 1) {
-            rc = aidax_render_host(e, a.stream, count, (int)a.n, a.in, a.out, AIDAX_LAYOUT_PLANAR, (size_t)stride);
+            rc = aidax_render_host_submit(e, a.stream, count, (int)a.n, a.in, a.out, AIDAX_LAYOUT_PLANAR, (size_t)stride);
         } else {
             rc = aidax_render_host(e, a.stream, 1, (int)a.n, a.in, a.out, AIDAX_LAYOUT_PLANAR, a.n);
         }
@@ -144,6 +170,33 @@ int render_pending(std::vector<EngineHub::Pending>& items)
     return 0;
 }
 
+// Called by the run() that completed chunk c (all of its live instances have parked).  If the parked ports are the
+// rows of one arena (the batch host's layout) the chunk goes to the GPU now; anything irregular is left to end().
+void submit_chunk(int c)
+{
+    const int lo = c * g_hub.chunk_streams, hi = std::min<int>(lo + g_hub.chunk_streams, (int)g_hub.slots.size());
+    const uint32_t epoch = g_hub.epoch;
+    int first = lo;
+    while (first < hi && g_hub.slots[first].epoch != epoch) ++first; // closed streams at the edges are fine
+    int last = hi;
+    while (last > first && g_hub.slots[last - 1].epoch != epoch) --last;
+    if (last - first < 2) return;
+    const EngineHub::Slot& a = g_hub.slots[first];
+    const ptrdiff_t stride = g_hub.slots[first + 1].in - a.in;
+    if (stride < (ptrdiff_t)a.n) return;
+    for (int s = first; s < last; ++s) {
+        const EngineHub::Slot& sl = g_hub.slots[s];
+        if (sl.epoch != epoch || sl.n != a.n || sl.in != a.in + (ptrdiff_t)(s - first) * stride || sl.out != a.out + (ptrdiff_t)(s - first) * stride)
+            return;
+    }
+    const int rc = aidax_render_host_submit(g_hub.engine, first, last - first, (int)a.n, a.in, a.out, AIDAX_LAYOUT_PLANAR, (size_t)stride);
+    if (rc != AIDAX_OK) {
+        g_hub.submit_error.store(rc, std::memory_order_relaxed);
+        return;
+    }
+    g_hub.chunks[c].submitted_epoch.store(epoch, std::memory_order_release);
+}
+
 int batch_end()
 {
     static std::vector<EngineHub::Pending> items; // reused across periods (the host calls end() from one thread)
@@ -151,13 +204,24 @@ int batch_end()
     {
         std::lock_guard<std::mutex> lk(g_hub.mu);
         g_hub.batching.store(false, std::memory_order_release);
-        const int hi = std::min<int>(g_hub.slot_hi.load(std::memory_order_acquire), (int)g_hub.slots.size());
-        for (int s = 0; s < hi; ++s) {
-            const EngineHub::Slot& sl = g_hub.slots[s];
-            if (sl.epoch == g_hub.epoch) items.push_back(EngineHub::Pending{s, sl.in, sl.out, sl.n});
+        const int n_slots = (int)g_hub.slots.size(), per_chunk = g_hub.chunk_streams / EngineHub::kBlockStreams;
+        for (int c = 0; c < g_hub.n_chunks; ++c) {
+            if (g_hub.chunks[c].submitted_epoch.load(std::memory_order_acquire) == g_hub.epoch) continue; // already on the GPU
+            for (int b = c * per_chunk; b < (c + 1) * per_chunk; ++b) {
+                if (g_hub.blocks[b].parked.load(std::memory_order_acquire) == 0) continue;
+                const int s1 = std::min(n_slots, (b + 1) * EngineHub::kBlockStreams);
+                for (int s = b * EngineHub::kBlockStreams; s < s1; ++s) {
+                    const EngineHub::Slot& sl = g_hub.slots[s];
+                    if (sl.epoch == g_hub.epoch) items.push_back(EngineHub::Pending{s, sl.in, sl.out, sl.n});
+                }
+            }
         }
     }
-    return render_pending(items);
+    int rc = render_pending(items);
+    const int rc_wait = g_hub.engine ? aidax_render_host_wait(g_hub.engine) : 0;
+    if (!rc) rc = rc_wait;
+    if (!rc) rc = g_hub.submit_error.load(std::memory_order_relaxed);
+    return rc;
 }
 
 uint64_t batch_launch_count() { return g_hub.engine ? aidax_engine_launch_count(g_hub.engine) : 0; }
@@ -167,14 +231,28 @@ const AidaxBatchInterface g_batch_iface = {
 };
 
 // ---------------------------------------------------------------------------- one plugin instance
-struct Plugin {
-    // ports
+// The fields run() touches on an ordinary period (no atom events, no control change) sit in the first three
+// cache lines: with hundreds of thousands of instances per period run() is bound by host memory traffic.
+struct alignas(64) Plugin {
+    // ---- hot
     const float* in = nullptr;
     float* out_1 = nullptr;
     const LV2_Atom_Sequence* control_port = nullptr;
     LV2_Atom_Sequence* notify_port = nullptr;
+    float* ctl_row = nullptr;        // set when control ports 4..24 are one contiguous float row (what a batch host connects)
+    aidax_engine* engine = nullptr;
+    int stream = -1;
+    int last_input_size = 0;         // rt-neural-generic.cpp:316
+    uint32_t notify_capacity = 0;    // atom.size of the notify port at the start of the last run() (:528-534)
+    LV2_URID urid_sequence = 0;
+    bool loading = true;             // :318
+    bool latched_valid = false;
+    bool latched_loading = true;
+    bool notify_armed = false;       // a run() has seen both atom ports: work_response may report (the reference's forge.buf != NULL)
+    bool forge_ready = false;        // the forge already points at this period's notify sequence
+    float latched[AIDAX_N_CONTROLS];
+    // ---- cold
     float* ctl[P_COUNT] = {};
-    // host features
     LV2_URID_Map* map = nullptr;
     LV2_Worker_Schedule* schedule = nullptr;
     LV2_Log_Log* log = nullptr;
@@ -182,17 +260,17 @@ struct Plugin {
     LV2_Atom_Forge forge{};
     LV2_Atom_Forge_Frame notify_frame{};
     Uris uris{};
-    // state
     double samplerate = 48000.0;
-    aidax_engine* engine = nullptr;
-    int stream = -1;
-    bool loading = true;      // rt-neural-generic.cpp:318
-    int last_input_size = 0;  // :316
     LoadedModel* model = nullptr;
-    float latched[AIDAX_N_CONTROLS];
-    bool latched_valid = false;
-    bool latched_loading = true;
 };
+
+// Points the forge at the notify port and opens the sequence, as run() does at :528-534.
+void open_notify_sequence(Plugin* self)
+{
+    lv2_atom_forge_set_buffer(&self->forge, (uint8_t*)self->notify_port, self->notify_capacity);
+    lv2_atom_forge_sequence_head(&self->forge, &self->notify_frame, 0);
+    self->forge_ready = true;
+}
 
 void map_uris(LV2_URID_Map* map, Uris* u)
 {
@@ -244,6 +322,7 @@ LV2_Handle instantiate(const LV2_Descriptor*, double samplerate, const char*, co
     map_uris(self->map, &self->uris);
     lv2_log_logger_init(&self->logger, self->map, self->log);
     lv2_atom_forge_init(&self->forge, self->map);
+    self->urid_sequence = self->uris.atom_Sequence;
 
     self->engine = hub_engine();
     if (!self->engine || aidax_stream_open(self->engine, samplerate, &self->stream) != AIDAX_OK) {
@@ -255,6 +334,8 @@ LV2_Handle instantiate(const LV2_Descriptor*, double samplerate, const char*, co
     {
         std::lock_guard<std::mutex> lk(g_hub.mu);
         g_hub.refs++;
+        if (g_hub.blocks[self->stream / EngineHub::kBlockStreams].live.fetch_add(1) == 0)
+            g_hub.chunks[self->stream / g_hub.chunk_streams].blocks_live.fetch_add(1);
     }
     self->loading = true;
     self->last_input_size = 0;
@@ -272,7 +353,12 @@ void connect_port(LV2_Handle instance, uint32_t port, void* data)
     case P_CONTROL: self->control_port = (const LV2_Atom_Sequence*)data; break;
     case P_NOTIFY: self->notify_port = (LV2_Atom_Sequence*)data; break;
     default:
-        if (port < P_COUNT) self->ctl[port] = (float*)data;
+        if (port < P_COUNT) {
+            self->ctl[port] = (float*)data;
+            bool row = self->ctl[P_IN_LPF] != nullptr;
+            for (uint32_t q = P_IN_LPF; row && q < P_COUNT; ++q) row = self->ctl[q] == self->ctl[P_IN_LPF] + (q - P_IN_LPF);
+            self->ctl_row = row ? self->ctl[P_IN_LPF] : nullptr;
+        }
         break;
     }
 }
@@ -290,47 +376,69 @@ void deactivate(LV2_Handle) {}
 void run(LV2_Handle instance, uint32_t n_samples)
 {
     Plugin* self = (Plugin*)instance;
-    const Uris* uris = &self->uris;
+    const Uris* uris = &self->uris; // (only read when the control port carries events)
 
     // control ports -> engine (only when something changed; the decode itself mirrors :489-517)
     float c[AIDAX_N_CONTROLS];
-    for (int i = 0; i < AIDAX_N_CONTROLS; ++i) {
-        const float* p = self->ctl[AIDAX_CTRL_PORT_BASE + i];
-        c[i] = (p && i != AIDAX_CTRL_MODELINSIZE) ? *p : 0.f;
+    if (self->ctl_row) {
+        memcpy(c, self->ctl_row, sizeof(c));
+        c[AIDAX_CTRL_MODELINSIZE] = 0.f;
+        // :518; stores that would not change memory are skipped throughout the ordinary-period path: a written line
+        // costs a write-back, and with ~400k instances per period run() is bound by host memory traffic
+        if (self->ctl_row[AIDAX_CTRL_MODELINSIZE] != (float)self->last_input_size) self->ctl_row[AIDAX_CTRL_MODELINSIZE] = (float)self->last_input_size;
+    } else {
+        for (int i = 0; i < AIDAX_N_CONTROLS; ++i) {
+            const float* p = self->ctl[AIDAX_CTRL_PORT_BASE + i];
+            c[i] = (p && i != AIDAX_CTRL_MODELINSIZE) ? *p : 0.f;
+        }
+        if (self->ctl[P_INPUT_SIZE]) *self->ctl[P_INPUT_SIZE] = (float)self->last_input_size; // :518
     }
-    if (self->ctl[P_INPUT_SIZE]) *self->ctl[P_INPUT_SIZE] = (float)self->last_input_size; // :518
 
     // atom messages (:526-586)
     if (self->notify_port && self->control_port) {
-        const uint32_t notify_capacity = self->notify_port->atom.size;
-        lv2_atom_forge_set_buffer(&self->forge, (uint8_t*)self->notify_port, notify_capacity);
-        lv2_atom_forge_sequence_head(&self->forge, &self->notify_frame, 0);
-        LV2_ATOM_SEQUENCE_FOREACH(self->control_port, ev)
-        {
-            if (!lv2_atom_forge_is_object_type(&self->forge, ev->body.type)) {
-                lv2_log_trace(&self->logger, "Unknown event type %d\n", ev->body.type);
-                continue;
+        const uint32_t capacity = self->notify_port->atom.size;
+        if (self->notify_capacity != capacity) self->notify_capacity = capacity;
+        if (!self->notify_armed) self->notify_armed = true;
+        if (self->control_port->atom.size <= sizeof(LV2_Atom_Sequence_Body)) {
+            // no events this period: leave what lv2_atom_forge_sequence_head leaves in the notify port (an empty
+            // sequence, if it fits) without touching the forge; work_response opens it on demand
+            if (self->notify_capacity >= sizeof(LV2_Atom_Sequence)) {
+                LV2_Atom_Sequence* ns = self->notify_port;
+                ns->atom.size = (uint32_t)sizeof(LV2_Atom_Sequence_Body);
+                ns->atom.type = self->urid_sequence;
+                ns->body.unit = 0;
+                ns->body.pad = 0;
             }
-            const LV2_Atom_Object* obj = (const LV2_Atom_Object*)&ev->body;
-            if (obj->body.otype != uris->patch_Set) {
-                lv2_log_trace(&self->logger, "Unknown object type %d\n", obj->body.otype);
-                continue;
+            if (self->forge_ready) self->forge_ready = false;
+        } else {
+            open_notify_sequence(self);
+            LV2_ATOM_SEQUENCE_FOREACH(self->control_port, ev)
+            {
+                if (!lv2_atom_forge_is_object_type(&self->forge, ev->body.type)) {
+                    lv2_log_trace(&self->logger, "Unknown event type %d\n", ev->body.type);
+                    continue;
+                }
+                const LV2_Atom_Object* obj = (const LV2_Atom_Object*)&ev->body;
+                if (obj->body.otype != uris->patch_Set) {
+                    lv2_log_trace(&self->logger, "Unknown object type %d\n", obj->body.otype);
+                    continue;
+                }
+                const LV2_Atom* property = nullptr;
+                const LV2_Atom* value = nullptr;
+                lv2_atom_object_get(obj, uris->patch_property, &property, uris->patch_value, &value, 0);
+                if (!property) { lv2_log_trace(&self->logger, "patch:Set message with no property\n"); continue; }
+                if (property->type != uris->atom_URID) { lv2_log_trace(&self->logger, "patch:Set property is not a URID\n"); continue; }
+                if (((const LV2_Atom_URID*)property)->body != uris->json) { lv2_log_trace(&self->logger, "patch:Set property body is not json\n"); continue; }
+                if (!value) { lv2_log_trace(&self->logger, "patch:Set message with no value\n"); continue; }
+                if (value->type != uris->atom_Path) { lv2_log_trace(&self->logger, "patch:Set value is not a Path\n"); continue; }
+                lv2_log_trace(&self->logger, "Queueing set message\n");
+                WorkerLoadMessage msg;
+                memset(&msg, 0, sizeof(msg));
+                msg.type = kWorkerLoad;
+                memcpy(msg.path, value + 1, std::min(value->size, (uint32_t)(sizeof(msg.path) - 1u)));
+                self->schedule->schedule_work(self->schedule->handle, sizeof(msg), &msg);
+                self->loading = true;
             }
-            const LV2_Atom* property = nullptr;
-            const LV2_Atom* value = nullptr;
-            lv2_atom_object_get(obj, uris->patch_property, &property, uris->patch_value, &value, 0);
-            if (!property) { lv2_log_trace(&self->logger, "patch:Set message with no property\n"); continue; }
-            if (property->type != uris->atom_URID) { lv2_log_trace(&self->logger, "patch:Set property is not a URID\n"); continue; }
-            if (((const LV2_Atom_URID*)property)->body != uris->json) { lv2_log_trace(&self->logger, "patch:Set property body is not json\n"); continue; }
-            if (!value) { lv2_log_trace(&self->logger, "patch:Set message with no value\n"); continue; }
-            if (value->type != uris->atom_Path) { lv2_log_trace(&self->logger, "patch:Set value is not a Path\n"); continue; }
-            lv2_log_trace(&self->logger, "Queueing set message\n");
-            WorkerLoadMessage msg;
-            memset(&msg, 0, sizeof(msg));
-            msg.type = kWorkerLoad;
-            memcpy(msg.path, value + 1, std::min(value->size, (uint32_t)(sizeof(msg.path) - 1u)));
-            self->schedule->schedule_work(self->schedule->handle, sizeof(msg), &msg);
-            self->loading = true;
         }
     }
 
@@ -347,9 +455,13 @@ void run(LV2_Handle instance, uint32_t n_samples)
     bool deferred = false;
     if (g_hub.batching.load(std::memory_order_acquire) && self->stream >= 0 && (size_t)self->stream < g_hub.slots.size()) {
         g_hub.slots[self->stream] = EngineHub::Slot{self->in, self->out_1, n_samples, g_hub.epoch};
-        int hi = g_hub.slot_hi.load(std::memory_order_relaxed);
-        while (hi <= self->stream && !g_hub.slot_hi.compare_exchange_weak(hi, self->stream + 1, std::memory_order_release, std::memory_order_relaxed)) {}
         deferred = true;
+        EngineHub::Block& bl = g_hub.blocks[self->stream / EngineHub::kBlockStreams];
+        if (bl.parked.fetch_add(1, std::memory_order_acq_rel) + 1 == bl.live.load(std::memory_order_relaxed)) {
+            const int c = self->stream / g_hub.chunk_streams;
+            EngineHub::Chunk& ch = g_hub.chunks[c];
+            if (ch.blocks_done.fetch_add(1, std::memory_order_acq_rel) + 1 == ch.blocks_live.load(std::memory_order_relaxed)) submit_chunk(c);
+        }
     }
     if (!deferred) {
         // lone instance: render this stream now and wait, so run() has LV2 semantics
@@ -370,6 +482,8 @@ void cleanup(LV2_Handle instance)
     {
         std::lock_guard<std::mutex> lk(g_hub.mu);
         g_hub.refs--;
+        if (g_hub.blocks[self->stream / EngineHub::kBlockStreams].live.fetch_sub(1) == 1)
+            g_hub.chunks[self->stream / g_hub.chunk_streams].blocks_live.fetch_sub(1);
     }
     delete self;
 }
@@ -471,7 +585,8 @@ LV2_Worker_Status work_response(LV2_Handle instance, uint32_t, const void* data)
     lv2_log_trace(&self->logger, "New model in use\n");
 
     // report the change to host/ui (write_set_file, uris.h:76-94)
-    if (self->forge.buf) {
+    if (self->notify_armed) {
+        if (!self->forge_ready) open_notify_sequence(self);
         lv2_atom_forge_frame_time(&self->forge, 0);
         LV2_Atom_Forge_Frame frame;
         lv2_atom_forge_object(&self->forge, &frame, 0, self->uris.patch_Set);

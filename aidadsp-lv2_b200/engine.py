@@ -74,6 +74,8 @@ def load_library():
     lib.aidax_stream_set_state.argtypes = [vp, C.c_int, fp, fp, C.POINTER(C.c_double)]
     lib.aidax_render_host.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_size_t]
     lib.aidax_render_device.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_size_t]
+    lib.aidax_render_host_submit.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_size_t]
+    lib.aidax_render_host_wait.argtypes = [vp]
     lib.aidax_engine_synchronize.argtypes = [vp]
     lib.aidax_host_alloc.argtypes = [C.c_size_t]
     lib.aidax_host_alloc.restype = vp
@@ -216,6 +218,14 @@ class Engine:
         self._chk(self.lib.aidax_render_host(self.h, first, n_streams, n_samples, x.ctypes.data, out.ctypes.data, layout, x.shape[1]))
         return out
 
+    def render_host_submit(self, x, out, first=0):
+        """Asynchronous half of render_host for a planar [n_streams][n_samples] block (x/out must outlive render_host_wait)."""
+        assert x.dtype == np.float32 and x.flags.c_contiguous and out.dtype == np.float32 and out.flags.c_contiguous
+        self._chk(self.lib.aidax_render_host_submit(self.h, first, x.shape[0], x.shape[1], x.ctypes.data, out.ctypes.data, LAYOUT_PLANAR, x.shape[1]))
+
+    def render_host_wait(self):
+        self._chk(self.lib.aidax_render_host_wait(self.h))
+
     def render_device(self, d_in, d_out, n_streams, n_samples, first=0, layout=LAYOUT_INTERLEAVED, stride=None):
         """d_in/d_out: device pointers (ints), e.g. torch_tensor.data_ptr().  Asynchronous."""
         if stride is None:
@@ -224,6 +234,17 @@ class Engine:
 
     def synchronize(self):
         self._chk(self.lib.aidax_engine_synchronize(self.h))
+
+
+def measure_pcie(device=0, nbytes=256 << 20):
+    """Pinned-memory copy rates in GB/s: (H2D alone, D2H alone, per direction with both at once)."""
+    lib = load_library()
+    lib.aidax_measure_pcie.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_double)]
+    v = (C.c_double * 3)()
+    rc = lib.aidax_measure_pcie(device, nbytes, v)
+    if rc != 0:
+        raise RuntimeError("aidax_measure_pcie: %s" % lib.aidax_last_error().decode())
+    return float(v[0]), float(v[1]), float(v[2])
 
 
 def measure_fp32_peak(device=0, millis=200):

@@ -279,6 +279,10 @@ def run_ours(args, rank, world, local_rank):
     except Exception:
         pass
     fp32_peak = engmod.measure_fp32_peak(local_rank, 200)
+    try:
+        pcie = engmod.measure_pcie(local_rank, 256 << 20)
+    except Exception:
+        pcie = None
     sample_ids = range(0, n_local, max(1, n_local // 64))
     flop_per_sample = sum(wl.flops_per_sample(first_global + s) for s in sample_ids) / len(sample_ids)
     flop_per_launch = flop_per_sample * n_local * T
@@ -335,8 +339,13 @@ def run_ours(args, rank, world, local_rank):
                    "us_per_buffer": round(e2e_s / e2e_steps * 1e6, 2), "steps": e2e_steps, "realtime_streams": int(e2e_value // FS),
                    "meets_deadline": bool(e2e_s / e2e_steps * 1e3 <= period_ms),
                    "phase_us": {"run_calls": round(e2e_phase_us[0], 1), "batch_end_copies_kernels_sync": round(e2e_phase_us[1], 1)},
-                   "path": "aidax-batch-host -> rt-neural-generic.so run() x N -> #batch end() -> aidax_render_host (pinned arena, chunked copy-in/kernel/copy-out pipeline)",
-                   "host_threads": host_threads, "timer": "wall clock (call returns after D2H + stream synchronise)"},
+                   "path": "aidax-batch-host -> rt-neural-generic.so run() x N (each completed chunk of instances is shipped at once: aidax_render_host_submit = pinned H2D -> kernels -> D2H on separate CUDA streams) -> #batch end() waits",
+                   "host_threads": host_threads, "timer": "wall clock (call returns after D2H + stream synchronise)",
+                   "pcie": None if pcie is None else {
+                       "h2d_gbs": round(pcie[0], 1), "d2h_gbs": round(pcie[1], 1), "duplex_gbs_per_direction": round(pcie[2], 1),
+                       "copy_floor_us": round(4 * T * n_local / (pcie[2] * 1e9) * 1e6, 1),
+                       "frac_of_copy_floor": round((4 * T * n_local / (pcie[2] * 1e9)) / (e2e_s / e2e_steps), 3),
+                       "note": "pinned-memory cudaMemcpyAsync rates measured in this run over 256 MiB; copy_floor = one period's bytes per direction at the duplex rate: the e2e period cannot be shorter"}},
            "gpu_launches": int(launches), "e2e_gpu_launches": int(e2e_launches), "clocks": clocks, "roofline": roofline}
 
     # ------------------------------------------------------------ configs[1] literal (1024 streams): the latency case

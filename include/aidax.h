@@ -208,6 +208,16 @@ int aidax_render_device(aidax_engine* e, int first_stream, int n_streams, int n_
                         const float* d_in, float* d_out, int layout, size_t stride);
 int aidax_engine_synchronize(aidax_engine* e);
 
+/* The two halves of aidax_render_host, for a host that hands a large period over in pieces while its
+ * instances are still running (the #batch extension does, include/aidax_batch.h): submit() enqueues the
+ * H2D copy, the kernels and the D2H copy of one stream range on the engine's copy/kernel streams and
+ * returns at once; wait() blocks until every range submitted since the last wait() is in its output
+ * buffer.  Ranges of one period must not overlap; the buffers must stay valid until wait() returns.
+ * Both may be called from any thread. */
+int aidax_render_host_submit(aidax_engine* e, int first_stream, int n_streams, int n_samples,
+                             const float* in, float* out, int layout, size_t stride);
+int aidax_render_host_wait(aidax_engine* e);
+
 /* Pinned host memory for audio arenas (cudaHostAlloc / cudaFreeHost). */
 void* aidax_host_alloc(size_t bytes);
 void aidax_host_free(void* p);
@@ -215,6 +225,10 @@ void aidax_host_free(void* p);
 /* Roofline denominator for the recurrence kernels: sustained FP32 FFMA throughput (TFLOP/s, 2 flop per
  * FFMA) of `device`, measured with a register-resident FFMA loop over all SMs for about `millis` ms. */
 int aidax_measure_fp32_peak(int device, int millis, double* tflops_out);
+
+/* Ceiling of the host-fed path (aidax_render_host): pinned-memory copy rates of `device` over a `bytes`-sized
+ * buffer, GB/s: [0] host->device alone, [1] device->host alone, [2] per direction with both running at once. */
+int aidax_measure_pcie(int device, size_t bytes, double gbs_out[3]);
 
 /* Number of kernel launches issued by the engine since creation (for bench accounting). */
 uint64_t aidax_engine_launch_count(aidax_engine* e);

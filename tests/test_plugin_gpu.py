@@ -203,3 +203,58 @@ def test_conditioned_hot_swap_vs_oracle(native_libs, tmp_path):
     assert ours.get_control("MODELINSIZE") == 3.0
     assert worst <= 1e-4, worst
     ours.close()
+
+
+_STREAMING_CHILD = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.environ["AIDAX_REPO"])
+import aidadsp_lv2_b200 as ax
+from aidadsp_lv2_b200 import signals
+N, T, NB = 1000, 128, 12
+path = sys.argv[1]
+host = ax.BatchHost(ax.plugin_path(), n_instances=N, max_block=T, n_threads=4)
+ctl = ax.default_controls(EQPOS=1.0, BASS=3.0, MID=-2.0, TREBLE=4.0)
+for port in range(4, 25):
+    if port != 23:
+        host.set_control(port, float(ctl[port - 4]))
+host.load_model(path)
+x = signals.sweep_noise_block(N, T * NB)
+yb = np.concatenate([host.process(x[:, b * T:(b + 1) * T]) for b in range(NB)], axis=1)
+launches = host.launch_count
+host.close()
+# the same periods through the engine API: one range, one call per period
+eng = ax.Engine(device=0, max_streams=N, max_block=T)
+mid, _ = eng.load_json(path)
+for _ in range(N):
+    s = eng.open_stream()
+    eng.set_controls(s, ctl, loading=True)
+ye = np.empty_like(x)
+for b in range(NB):
+    if b == 1:   # the plugin binds the model after the first period's worker round trip
+        for s in range(N):
+            eng.set_model(s, mid)
+            eng.set_controls(s, ctl, loading=False)
+    ye[:, b * T:(b + 1) * T] = eng.render_host(np.ascontiguousarray(x[:, b * T:(b + 1) * T]))
+eng.close()
+err = float(np.abs(yb - ye).max())
+print("RESULT", err, launches, float(np.abs(yb).max()))
+"""
+
+
+def test_streaming_chunk_handover_equals_single_render(native_libs, tmp_path):
+    """The #batch extension ships a chunk of instances to the GPU as soon as the chunk's last run() returned
+    (aidax_render_host_submit) while other host threads are still inside run().  With a 256-stream chunk, 1000 instances
+    on 4 host threads take 4 chunk submissions per period; the audio must equal one aidax_render_host call per period."""
+    import subprocess
+    import sys
+    child = tmp_path / "child.py"
+    child.write_text(_STREAMING_CHILD)
+    env = dict(os.environ, AIDAX_BATCH_CHUNK="256", AIDAX_REPO=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, str(child), bundled_model_paths()[0]], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][-1].split()
+    err, launches, peak = float(line[1]), int(line[2]), float(line[3])
+    assert peak > 1e-3
+    assert launches >= 4 * 11, "expected one launch per 256-stream chunk per period, saw %d launches" % launches
+    assert err <= 2e-6, "chunked hand-over differs from a single render: %g" % err
