@@ -24,6 +24,13 @@
 #include "kernels.cuh"
 #include "tc_prims.cuh"
 
+// Timing experiments only (tools/whatif.sh builds scratch libraries with -DAIDAX_WHATIF=<bits>; results are wrong by
+// construction): 1 = no MMA issue / completion wait, 2 = MUFU replaced by FMUL, 4 = no exponent clamps,
+// 8 = no filter/gain stages.
+#ifndef AIDAX_WHATIF
+#define AIDAX_WHATIF 0
+#endif
+
 namespace aidax {
 
 template <int H>
@@ -57,67 +64,106 @@ struct TcShape {
 struct TcTile {
     float* a_hi;         // this thread's row in the A operand: a_hi + chunk*512 is a float4 slot
     float* a_lo;
-    uint32_t a_hi_addr;  // shared-space byte addresses of the tile's A (hi, lo) and the CTA's B (hi, lo)
-    uint32_t a_lo_addr;
-    uint32_t b_hi_addr;
-    uint32_t b_lo_addr;
+    uint64_t da_hi;      // shared-memory matrix descriptors of the tile's A (hi, lo) and the CTA's B (hi, lo) at K step 0
+    uint64_t da_lo;
+    uint64_t db_hi;
+    uint64_t db_lo;
     uint32_t bar_addr;   // the tile's mbarrier
     uint32_t phase;      // its current parity
     uint32_t tmem_d;     // TMEM address of the tile's accumulator (lane 0)
     uint32_t tmem_ld;    // same, with this warp's lane quadrant
     uint32_t bar_id;     // named barrier of the tile's 128 threads
     const float* dw;     // dense weights [H] + bias
-    bool leader;
+    bool issuer;         // warp-uniform: this warp issues the tile's MMAs (one elected lane)
 };
 
 template <int CELL, int H, int MATH>
 struct TcCell {
     using S = TcShape<H>;
 
+    __device__ __forceinline__ static void store_chunk(const TcTile& tt, int chunk, float2 v01, float2 v23)
+    {
+        // 3xTF32 split (tc::split_tf32) of four values, the subtraction packed
+        const float2 h01 = make_float2(__uint_as_float(__float_as_uint(v01.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v01.y) & 0xFFFFE000u));
+        const float2 h23 = make_float2(__uint_as_float(__float_as_uint(v23.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v23.y) & 0xFFFFE000u));
+        const float2 d01 = tc::sub2(v01, h01), d23 = tc::sub2(v23, h23);
+        *reinterpret_cast<float4*>(tt.a_hi + chunk * 512) = make_float4(h01.x, h01.y, h23.x, h23.y);
+        *reinterpret_cast<float4*>(tt.a_lo + chunk * 512) =
+            make_float4(__uint_as_float(__float_as_uint(d01.x) + 0x1000u), __uint_as_float(__float_as_uint(d01.y) + 0x1000u),
+                        __uint_as_float(__float_as_uint(d23.x) + 0x1000u), __uint_as_float(__float_as_uint(d23.y) + 0x1000u));
+    }
     __device__ __forceinline__ static void store_chunk(const TcTile& tt, int chunk, float v0, float v1, float v2, float v3)
     {
-        float h0, h1, h2, h3, l0, l1, l2, l3;
-        tc::split_tf32(v0, h0, l0);
-        tc::split_tf32(v1, h1, l1);
-        tc::split_tf32(v2, h2, l2);
-        tc::split_tf32(v3, h3, l3);
-        *reinterpret_cast<float4*>(tt.a_hi + chunk * 512) = make_float4(h0, h1, h2, h3);
-        *reinterpret_cast<float4*>(tt.a_lo + chunk * 512) = make_float4(l0, l1, l2, l3);
+        store_chunk(tt, chunk, make_float2(v0, v1), make_float2(v2, v3));
     }
 
+    // Issued by ONE elected thread of the tile's first warp.  The four base descriptors are warp-uniform values
+    // prepared once per kernel; a K step only adds a constant to the descriptor's address field.
     __device__ __forceinline__ static void issue_mmas(const TcTile& tt)
     {
         constexpr uint32_t idesc = tc::make_idesc_tf32(128, S::NMMA);
-        constexpr uint32_t LBO_A = 128 * 16, LBO_B = S::N * 16, SBO = 128;
+        constexpr uint32_t LBO_A = 128 * 16, LBO_B = S::N * 16;
 #pragma unroll
         for (int ks = 0; ks < S::KSTEPS; ++ks) {
-            const uint32_t ao = ks * 2 * LBO_A, bo = ks * 2 * LBO_B;
+            const uint64_t ao = (ks * 2 * LBO_A) >> 4, bo = (ks * 2 * LBO_B) >> 4;
 #pragma unroll
             for (int nh = 0; nh < S::NSPLIT; ++nh) {
-                const uint32_t d = tt.tmem_d + nh * S::NMMA, bn = bo + nh * S::NMMA * 16;
+                const uint32_t d = tt.tmem_d + nh * S::NMMA;
+                const uint64_t bn = bo + ((nh * S::NMMA * 16) >> 4);
                 // smallest terms first
-                tc::mma_tf32(d, tc::make_smem_desc(tt.a_lo_addr + ao, LBO_A, SBO), tc::make_smem_desc(tt.b_hi_addr + bn, LBO_B, SBO), idesc, ks > 0);
-                tc::mma_tf32(d, tc::make_smem_desc(tt.a_hi_addr + ao, LBO_A, SBO), tc::make_smem_desc(tt.b_lo_addr + bn, LBO_B, SBO), idesc, 1);
-                tc::mma_tf32(d, tc::make_smem_desc(tt.a_hi_addr + ao, LBO_A, SBO), tc::make_smem_desc(tt.b_hi_addr + bn, LBO_B, SBO), idesc, 1);
+                tc::mma_tf32(d, tt.da_lo + ao, tt.db_hi + bn, idesc, ks > 0);
+                tc::mma_tf32(d, tt.da_hi + ao, tt.db_lo + bn, idesc, 1);
+                tc::mma_tf32(d, tt.da_hi + ao, tt.db_hi + bn, idesc, 1);
             }
         }
         tc::mma_commit(tt.bar_addr);
     }
 
-    // 1/a, 1/b, 1/c, 1/d from ONE MUFU.RCP (a..d in [1, 2^24+1]: no overflow, ~3 ulp): the kernel is bound by the
-    // XU (MUFU) pipe, so reciprocals are batched four at a time and the extra multiplies go to the idle FMA pipe.
-    __device__ __forceinline__ static void inv4(float a, float b, float c, float d, float& ia, float& ib, float& ic, float& id)
+    // accumulator column of (hidden unit u, gate lane g).  Within a 16-column chunk of 4 units the order is
+    // [g0:u0 u1 | g1:u0 u1 | g2:u0 u1 | g3:u0 u1 | g0:u2 u3 | ... ] so registers (2j, 2j+1) of one tcgen05.ld hold the SAME
+    // gate of two neighbouring units: an aligned register pair is directly one packed-fp32 (f32x2) operand.
+    __host__ __device__ static constexpr int column_of(int u, int g) { return 16 * (u / 4) + 8 * ((u % 4) / 2) + 2 * g + (u % 2); }
+    __host__ __device__ static constexpr int unit_of_column(int n) { return 4 * (n / 16) + 2 * ((n % 16) / 8) + (n % 2); }
+    __host__ __device__ static constexpr int gate_of_column(int n) { return (n % 8) / 2; }
+
+    __device__ __forceinline__ static float2 pair(const uint32_t (&raw)[16], int j)
     {
-        const float ab = a * b, cd = c * d;
-        const float r = rcp_approx(ab * cd);
-        const float rab = r * cd, rcd = r * ab;
-        ia = rab * b; ib = rab * a; ic = rcd * d; id = rcd * c;
+        return make_float2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
+    }
+#if AIDAX_WHATIF & 2
+    __device__ __forceinline__ static float2 rcp2(float2 a) { return tc::mul2(a, tc::splat2(0.999f)); }
+#else
+    __device__ __forceinline__ static float2 rcp2(float2 a) { return make_float2(rcp_approx(a.x), rcp_approx(a.y)); }
+#endif
+    // 1/a, 1/b, 1/c, 1/d from ONE MUFU.RCP per lane of the pair (a..d in [1, 2^24+1]: no overflow, ~3 ulp): the kernel
+    // is bound by the XU (MUFU) pipe and by issue slots, so reciprocals are batched four at a time and the extra
+    // multiplies run as packed FMUL2 (two hidden units per instruction) on the otherwise idle FMA pipe.
+    __device__ __forceinline__ static void inv4(float2 a, float2 b, float2 c, float2 d, float2& ia, float2& ib, float2& ic, float2& id)
+    {
+        const float2 ab = tc::mul2(a, b), cd = tc::mul2(c, d);
+        const float2 r = rcp2(tc::mul2(ab, cd));
+        const float2 rab = tc::mul2(r, cd), rcd = tc::mul2(r, ab);
+        ia = tc::mul2(rab, b); ib = tc::mul2(rab, a); ic = tc::mul2(rcd, d); id = tc::mul2(rcd, c);
+    }
+    __device__ __forceinline__ static void inv2(float2 a, float2 b, float2& ia, float2& ib)
+    {
+        const float2 r = rcp2(tc::mul2(a, b));
+        ia = tc::mul2(r, b); ib = tc::mul2(r, a);
     }
     // 1 + 2^e, exponent clamped so that four of them can be multiplied without overflow
     // (sigmoid(-16.6) = 6e-8, 1 - tanh(8.3) = 1.2e-7: the clamp is below fp32 resolution of the results)
-    __device__ __forceinline__ static float one_plus_exp2(float e) { return 1.0f + ex2_approx(fminf(e, 24.0f)); }
+    __device__ __forceinline__ static float2 one_plus_exp2(float2 e)
+    {
+#if AIDAX_WHATIF & 2
+        return tc::add2(tc::mul2(make_float2(fminf(e.x, 24.0f), fminf(e.y, 24.0f)), tc::splat2(0.001f)), tc::splat2(1.0f));
+#elif AIDAX_WHATIF & 4
+        return tc::add2(make_float2(ex2_approx(e.x), ex2_approx(e.y)), tc::splat2(1.0f));
+#else
+        return tc::add2(make_float2(ex2_approx(fminf(e.x, 24.0f)), ex2_approx(fminf(e.y, 24.0f))), tc::splat2(1.0f));
+#endif
+    }
     // In fast-math mode the B operand's columns are pre-scaled so that the accumulator IS that exponent:
-    // sigmoid(x) = 1/(1 + 2^(-x log2 e)), tanh(x) = 1 - 2/(1 + 2^(2x log2 e)).  Column order per unit: LSTM i,f,g,o;
+    // sigmoid(x) = 1/(1 + 2^(-x log2 e)), tanh(x) = 1 - 2/(1 + 2^(2x log2 e)).  Gate lanes per unit: LSTM i,f,g,o;
     // GRU z, r, Uh.h+bh1, Wh.x+bh0 (the last two are summed as r*a2 + a3 before the tanh, so both carry its scale).
     __host__ __device__ static constexpr float column_scale(int g)
     {
@@ -172,68 +218,78 @@ struct TcCell {
         }
     }
 
-    // gate nonlinearities + cell update of the 4 hidden units whose 16 accumulator columns are in `raw`
-    __device__ __forceinline__ static void eval_chunk(const uint32_t (&raw)[16], int q, float (&cst)[H], float (&hn)[4])
+    // Gate nonlinearities + cell update of the 4 (TWO: 8) hidden units whose accumulator columns are in raw0 (and raw1),
+    // two units per packed instruction.  hn[2c], hn[2c+1] = new h of the units (4(q+c), +1) and (4(q+c)+2, +3).
+    template <bool TWO>
+    __device__ __forceinline__ static void eval_group(const uint32_t (&raw0)[16], const uint32_t (&raw1)[16], int q, float (&cst)[H],
+                                                      float2 (&hn)[4])
     {
         constexpr float L2E = 1.4426950408889634f;
-        float a[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(raw[i]);
+        constexpr int NP = TWO ? 4 : 2; // unit pairs in the group
+        const float2 one = tc::splat2(1.0f), m2 = tc::splat2(-2.0f);
         if (MATH == 0 && CELL == 0) {
             // LSTM, RTN/lstm/lstm_xsimd.h:193-213, 271-283: c' = i*tanh(g) + f*c ; h' = o*tanh(c')
-            float og[4], e4[4];
+            float2 og[NP], ec[NP], t[NP];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int u = 4 * q + i;
-                float ii, fi, gi;
-                inv4(one_plus_exp2(a[4 * i]), one_plus_exp2(a[4 * i + 1]), one_plus_exp2(a[4 * i + 2]), one_plus_exp2(a[4 * i + 3]),
-                     ii, fi, gi, og[i]);
-                const float c = fmaf(ii, fmaf(-2.f, gi, 1.f), fi * cst[u]);
-                cst[u] = c;
-                e4[i] = one_plus_exp2(c * (2.f * L2E));
+            for (int pr = 0; pr < NP; ++pr) {
+                const uint32_t(&raw)[16] = pr < 2 ? raw0 : raw1;
+                const int j0 = 4 * (pr & 1), u = 4 * q + 2 * pr;
+                float2 ii, fi, gi;
+                inv4(one_plus_exp2(pair(raw, j0)), one_plus_exp2(pair(raw, j0 + 1)), one_plus_exp2(pair(raw, j0 + 2)),
+                     one_plus_exp2(pair(raw, j0 + 3)), ii, fi, gi, og[pr]);
+                const float2 c = tc::fma2(ii, tc::fma2(m2, gi, one), tc::mul2(fi, make_float2(cst[u], cst[u + 1])));
+                cst[u] = c.x;
+                cst[u + 1] = c.y;
+                ec[pr] = one_plus_exp2(tc::mul2(c, tc::splat2(2.f * L2E)));
             }
-            float t0, t1, t2, t3;
-            inv4(e4[0], e4[1], e4[2], e4[3], t0, t1, t2, t3);
-            hn[0] = og[0] * fmaf(-2.f, t0, 1.f);
-            hn[1] = og[1] * fmaf(-2.f, t1, 1.f);
-            hn[2] = og[2] * fmaf(-2.f, t2, 1.f);
-            hn[3] = og[3] * fmaf(-2.f, t3, 1.f);
+            if constexpr (TWO) inv4(ec[0], ec[1], ec[2], ec[3], t[0], t[1], t[2], t[3]);
+            else inv2(ec[0], ec[1], t[0], t[1]);
+#pragma unroll
+            for (int pr = 0; pr < NP; ++pr) hn[pr] = tc::mul2(og[pr], tc::fma2(m2, t[pr], one));
         } else if (MATH == 0) {
             // GRU, RTN/gru/gru_xsimd.h:219-239, 265-271: h' = (1-z)*tanh(r*(Uh.h+bh1) + Wh.x+bh0) + z*h
-            float z[4], e4[4];
+            float2 z[NP], e[NP], t[NP];
 #pragma unroll
-            for (int i = 0; i < 4; i += 2) {
-                float r0, r1;
-                inv4(one_plus_exp2(a[4 * i]), one_plus_exp2(a[4 * i + 1]), one_plus_exp2(a[4 * i + 4]), one_plus_exp2(a[4 * i + 5]),
-                     z[i], r0, z[i + 1], r1);
-                e4[i] = one_plus_exp2(fmaf(r0, a[4 * i + 2], a[4 * i + 3]));
-                e4[i + 1] = one_plus_exp2(fmaf(r1, a[4 * i + 6], a[4 * i + 7]));
+            for (int c4 = 0; c4 < NP / 2; ++c4) {
+                const uint32_t(&raw)[16] = c4 == 0 ? raw0 : raw1;
+                float2 r0, r1;
+                inv4(one_plus_exp2(pair(raw, 0)), one_plus_exp2(pair(raw, 1)), one_plus_exp2(pair(raw, 4)), one_plus_exp2(pair(raw, 5)),
+                     z[2 * c4], r0, z[2 * c4 + 1], r1);
+                e[2 * c4] = one_plus_exp2(tc::fma2(r0, pair(raw, 2), pair(raw, 3)));
+                e[2 * c4 + 1] = one_plus_exp2(tc::fma2(r1, pair(raw, 6), pair(raw, 7)));
             }
-            float t4[4];
-            inv4(e4[0], e4[1], e4[2], e4[3], t4[0], t4[1], t4[2], t4[3]);
+            if constexpr (TWO) inv4(e[0], e[1], e[2], e[3], t[0], t[1], t[2], t[3]);
+            else inv2(e[0], e[1], t[0], t[1]);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int u = 4 * q + i;
-                const float hh = fmaf(-2.f, t4[i], 1.f);
-                hn[i] = fmaf(1.0f - z[i], hh, z[i] * cst[u]);
-                cst[u] = hn[i];
+            for (int pr = 0; pr < NP; ++pr) {
+                const int u = 4 * q + 2 * pr;
+                const float2 hh = tc::fma2(m2, t[pr], one);
+                hn[pr] = tc::fma2(tc::sub2(one, z[pr]), hh, tc::mul2(z[pr], make_float2(cst[u], cst[u + 1])));
+                cst[u] = hn[pr].x;
+                cst[u + 1] = hn[pr].y;
             }
         } else {
+            // precise math (expf / tanhf / IEEE division), scalar
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int u = 4 * q + i;
+            for (int i = 0; i < 2 * NP; ++i) {
+                const uint32_t(&raw)[16] = i < 4 ? raw0 : raw1;
+                const int u = 4 * q + i, cb = 8 * ((i & 3) / 2) + (i & 1); // column of gate g: cb + 2g
+                const float a0 = __uint_as_float(raw[cb]), a1 = __uint_as_float(raw[cb + 2]);
+                const float a2 = __uint_as_float(raw[cb + 4]), a3 = __uint_as_float(raw[cb + 6]);
+                float h;
                 if (CELL == 0) {
-                    const float ig = sigmoid_f<1>(a[4 * i]), fg = sigmoid_f<1>(a[4 * i + 1]);
-                    const float gg = tanh_f<1>(a[4 * i + 2]), og = sigmoid_f<1>(a[4 * i + 3]);
+                    const float ig = sigmoid_f<1>(a0), fg = sigmoid_f<1>(a1), gg = tanh_f<1>(a2), og = sigmoid_f<1>(a3);
                     const float c = fmaf(ig, gg, fg * cst[u]);
                     cst[u] = c;
-                    hn[i] = og * tanh_f<1>(c);
+                    h = og * tanh_f<1>(c);
                 } else {
-                    const float zg = sigmoid_f<1>(a[4 * i]), rg = sigmoid_f<1>(a[4 * i + 1]);
-                    const float hh = tanh_f<1>(fmaf(rg, a[4 * i + 2], a[4 * i + 3]));
-                    hn[i] = fmaf(1.0f - zg, hh, zg * cst[u]);
-                    cst[u] = hn[i];
+                    const float zg = sigmoid_f<1>(a0), rg = sigmoid_f<1>(a1);
+                    const float hh = tanh_f<1>(fmaf(rg, a2, a3));
+                    h = fmaf(1.0f - zg, hh, zg * cst[u]);
+                    cst[u] = h;
                 }
+                if (i & 1) hn[i / 2].y = h;
+                else hn[i / 2].x = h;
             }
         }
     }
@@ -257,17 +313,22 @@ struct TcCell {
             tc::fence_proxy_async();
             tc::tc_fence_before();
             tc::bar_sync(tt.bar_id, 128);
-            if (tt.leader) {
-                tc::tc_fence_after();
-                issue_mmas(tt);
+#if !(AIDAX_WHATIF & 1)
+            if (tt.issuer) {
+                if (tc::elect_one()) {
+                    tc::tc_fence_after();
+                    issue_mmas(tt);
+                }
+                __syncwarp();
             }
             tc::mbar_wait(tt.bar_addr, tt.phase);
             tt.phase ^= 1u;
+#endif
             tc::tc_fence_after();
 
             // epilogue: groups of two 16-column chunks (8 hidden units) are loaded together and evaluated as one
             // straight-line block, so the 8 + 2 batched reciprocal chains of a group overlap each other's MUFU latency
-            float y0 = db, y1 = 0.f;
+            float2 y2 = make_float2(db, 0.f);
 #pragma unroll
             for (int q = 0; q < H / 4; q += 2) {
                 constexpr int NQ = H / 4;
@@ -276,23 +337,26 @@ struct TcCell {
                 tc::tmem_ld16(tt.tmem_ld + 16 * q, raw0);
                 if (two) tc::tmem_ld16(tt.tmem_ld + 16 * (q + 1), raw1);
                 tc::tmem_ld_wait16(raw0);
-                float hn0[4], hn1[4];
-                eval_chunk(raw0, q, cst, hn0);
+                float2 hn[4];
                 if (two) {
                     tc::tmem_ld_wait16(raw1); // already complete (one wait covers all outstanding loads); keeps the asm ordering explicit
-                    eval_chunk(raw1, q + 1, cst, hn1);
+                    eval_group<true>(raw0, raw1, q, cst, hn);
+                } else {
+                    eval_group<false>(raw0, raw0, q, cst, hn);
                 }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    y0 = fmaf(tt.dw[4 * q + i], hn0[i], y0);
-                    if (two) y1 = fmaf(tt.dw[4 * q + 4 + i], hn1[i], y1);
+                const float2* dw2 = reinterpret_cast<const float2*>(tt.dw + 4 * q);
+                y2 = tc::fma2(dw2[0], hn[0], y2);
+                y2 = tc::fma2(dw2[1], hn[1], y2);
+                store_chunk(tt, q, hn[0], hn[1]);
+                if (two) {
+                    y2 = tc::fma2(dw2[2], hn[2], y2);
+                    y2 = tc::fma2(dw2[3], hn[3], y2);
+                    store_chunk(tt, q + 1, hn[2], hn[3]);
                 }
-                store_chunk(tt, q, hn0[0], hn0[1], hn0[2], hn0[3]);
-                if (two) store_chunk(tt, q + 1, hn1[0], hn1[1], hn1[2], hn1[3]);
             }
             // dense + skip + output gain (applyModel, rt-neural-generic.cpp:170-182)
             if (xcol && commit) {
-                const float y = y0 + y1;
+                const float y = y2.x + y2.y;
                 xcol[t * XP] = (in_skip ? xg + y : y) * out_gain;
             }
         }
@@ -313,7 +377,8 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
     extern __shared__ __align__(128) float smem_tc[];
     float* smem = smem_tc;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0); // broadcast: the compiler may treat it as warp-uniform
     const int tile = warp >> 2, r = tid & 127;
     const int blk = blockIdx.x;
     const StreamArrays& sa = p.sa;
@@ -329,16 +394,17 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
     const int input_size = md.input_size;
     const int n_ptiles = input_size - 1;
 
-    // ---- B operand (hi, lo) from the packed weight block (layout.h): B[n = 4*unit + lane][k]
+    // ---- B operand (hi, lo) from the packed weight block (layout.h): B[n = column_of(unit, gate)][k]
     {
         const float* wk = md.weights;
         const float* bias = wk + (H + 3) * H * 4;
         for (int idx = tid; idx < S::N * S::KP; idx += NTHREADS) {
             const int n = idx % S::N, k = idx / S::N;
+            const int g = Cell::gate_of_column(n), src = 4 * Cell::unit_of_column(n) + g; // packed block: column 4*unit + gate
             float w = 0.f;
-            if (k < H + 3) w = __ldg(wk + (size_t)k * S::N + n);
-            else if (k == H + 3) w = __ldg(bias + n);
-            if (MATH == 0) w *= Cell::column_scale(n & 3); // the accumulator is directly the exponent of 2 the gate needs
+            if (k < H + 3) w = __ldg(wk + (size_t)k * S::N + src);
+            else if (k == H + 3) w = __ldg(bias + src);
+            if (MATH == 0) w *= Cell::column_scale(g); // the accumulator is directly the exponent of 2 the gate needs
             float hi, lo;
             tc::split_tf32(w, hi, lo);
             const int off = (k >> 2) * (S::N * 4) + n * 4 + (k & 3);
@@ -364,17 +430,21 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
     TcTile tt;
     tt.a_hi = Abase + tile * 2 * S::A_FLOATS + r * 4;
     tt.a_lo = tt.a_hi + S::A_FLOATS;
-    tt.a_hi_addr = tc::smem_u32(Abase + tile * 2 * S::A_FLOATS);
-    tt.a_lo_addr = tt.a_hi_addr + S::A_FLOATS * 4;
-    tt.b_hi_addr = tc::smem_u32(Bh);
-    tt.b_lo_addr = tc::smem_u32(Bl);
+    {
+        constexpr uint32_t LBO_A = 128 * 16, LBO_B = S::N * 16, SBO = 128;
+        const uint32_t a_addr = tc::smem_u32(Abase + tile * 2 * S::A_FLOATS);
+        tt.da_hi = tc::make_smem_desc(a_addr, LBO_A, SBO);
+        tt.da_lo = tc::make_smem_desc(a_addr + S::A_FLOATS * 4, LBO_A, SBO);
+        tt.db_hi = tc::make_smem_desc(tc::smem_u32(Bh), LBO_B, SBO);
+        tt.db_lo = tc::make_smem_desc(tc::smem_u32(Bl), LBO_B, SBO);
+    }
     tt.bar_addr = tc::smem_u32(&bars[tile]);
     tt.phase = 0;
     tt.tmem_d = tmem_base + tile * S::N;
     tt.tmem_ld = tt.tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
     tt.bar_id = 1 + tile;
     tt.dw = dw;
-    tt.leader = r == 0;
+    tt.issuer = (warp & 3) == 0;
 
     float* wbase = smem + ((S::fixed_floats(NT) + 3) & ~3) + (size_t)warp * S::warp_floats(p.ts, n_ptiles);
     int* wslots = reinterpret_cast<int*>(wbase);
@@ -417,7 +487,7 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
         __syncwarp();
 
         // ---- stages before the network (run(), rt-neural-generic.cpp:622-644)
-        if (cslot >= 0 && enabled) {
+        if (cslot >= 0 && enabled && !(AIDAX_WHATIF & 8)) {
             float* xcol = xbuf + lane;
             pass_lpf_pregain<XP>(xcol, ts, sa, cslot, (flags & F_LPF) != 0);
             if (flags & F_EQ_PRE) pass_eq<XP>(xcol, ts, sa, cslot, (flags & F_EQ_BANDPASS) != 0);
@@ -441,7 +511,7 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
                       md.out_gain, md.in_skip != 0, net_on);
 
         // ---- stages after the network (:645-655)
-        if (cslot >= 0 && enabled) {
+        if (cslot >= 0 && enabled && !(AIDAX_WHATIF & 8)) {
             float* xcol = xbuf + lane;
             const bool dc_on = (flags & F_DC) != 0;
             if (flags & F_EQ_POST) {

@@ -76,6 +76,20 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N)
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] . B[smem]^T, issued by ONE thread for the whole CTA
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
@@ -125,6 +139,44 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo)
     hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
     lo = __uint_as_float(__float_as_uint(x - hi) + 0x1000u);
 }
+
+// ---- packed fp32 pairs (sm_100 FMUL2 / FADD2 / FFMA2): two IEEE round-to-nearest operations per issue slot.
+// The gate epilogue is bound by issue slots and the XU pipe, not by FMA-pipe throughput, so its fp32 arithmetic
+// runs two hidden units per instruction.  Each half is bit-identical to the scalar mul.rn / add.rn / fma.rn.
+__device__ __forceinline__ float2 mul2(float2 a, float2 b)
+{
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b)
+{
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b)
+{
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tsub.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
+{
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 
 } // namespace tc
 } // namespace aidax
