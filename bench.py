@@ -318,7 +318,8 @@ def run_ours(args, rank, world, local_rank):
                 "achieved": round(achieved_tflops, 3), "peak": round(fp32_peak, 2), "unit": "TFLOP/s", "frac": round(achieved_tflops / fp32_peak, 4),
                 "peak_source": "FFMA loop measured in this run (aidax_measure_fp32_peak); FP32 CUDA-core peak is not in MEASURED_PEAKS.json",
                 "flop_per_stream_sample": round(flop_per_sample, 1), "launch_ms": round(kernel_ms, 5),
-                "launches_per_step": launches_per_step, "traffic": traffic, "pipes": pipes,
+                "launches_per_step": launches_per_step,
+                "traffic": None if traffic is None else traffic["bytes_per_launch"], "traffic_detail": traffic, "pipes": pipes,
                 "hbm": {"achieved": round(io_gbs, 2), "peak": hbm_peak, "unit": "GB/s", "frac": round(io_gbs / hbm_peak, 5),
                         "peak_source": "MEASURED_PEAKS.json (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)", "algorithmic_bytes_per_stream_sample": 8}}
 

@@ -96,3 +96,59 @@ def test_partial_render_ranges_and_reopen(native_libs):
         assert np.abs(np.concatenate([lo, hi]) - full).max() <= 2e-6
     eng.close()
     ref.close()
+
+
+@pytest.mark.parametrize("name,n", [("c3", 8192), ("c4", 65536), ("c5", 262144), ("c2", 378880)])
+def test_full_size_configs(native_libs, name, n):
+    """BASELINE.json's literal stream counts (and the bench's GPU-filling C2 count) on one GPU, device-resident
+    stream-interleaved buffers.  The oracle cannot render that many streams, so parity at full size is:
+      (i) a deterministic subset of streams spanning every model and both ends of the batch against the oracle
+          (<= 1e-4, north_star tolerance), and
+     (ii) the size-independent property: the batch is built from 256 distinct input signals repeated, so two streams
+          with the same model, controls and input must agree bit for bit wherever they sit in the launch."""
+    import torch
+    wl = workloads.get(name, n)
+    eng = ax.Engine(max_streams=n, max_block=T)
+    _setup(eng, wl, n)
+    NB, P = 4, 256
+    base = signals.sweep_noise_block(P, T * NB)                      # [P][T*NB]; stream s plays base[s % P]
+    n_models = len(wl.models)
+    per_model = max(1, 24 // n_models)
+    check = {0, n - 1, n // 2}
+    for m in range(n_models):
+        lo, hi = (m * n + n_models - 1) // n_models, ((m + 1) * n + n_models - 1) // n_models
+        check.update(int(v) for v in np.linspace(lo, hi - 1, per_model + 1))
+    check = sorted(check)
+    orcs = {s: _oracle_stream(wl, s, n) for s in check}
+    p1 = signals.triangle(1.0, NB, T)
+    p2 = signals.triangle(1.7, NB, T)
+    reps = (n + P - 1) // P
+    worst = 0.0
+    for b in range(NB):
+        c = wl.controls.copy()
+        if wl.automate_params:
+            # per-stream phase repeats with the input signal so that property (ii) still holds
+            ph = (np.arange(n) % P).astype(np.float32) * 0.01
+            a1, a2 = np.mod(p1[b] + ph, 1.0).astype(np.float32), np.mod(p2[b] + ph, 1.0).astype(np.float32)
+            eng.set_params(0, a1, a2)
+        xb = torch.from_numpy(np.ascontiguousarray(base[:, b * T:(b + 1) * T].T)).cuda().repeat(1, reps)[:, :n].contiguous()  # [T][n]
+        yb = torch.empty_like(xb)
+        eng.render_device(xb.data_ptr(), yb.data_ptr(), n, T, layout=ax.LAYOUT_INTERLEAVED)
+        eng.synchronize()
+        assert bool(torch.isfinite(yb).all())
+        # (ii) streams P apart inside one model's run are replicas of each other
+        for m in range(n_models):
+            lo, hi = (m * n + n_models - 1) // n_models, ((m + 1) * n + n_models - 1) // n_models
+            k = (hi - lo) // P
+            if k >= 2:
+                blk = yb[:, lo:lo + k * P].reshape(T, k, P)
+                assert bool((blk == blk[:, :1, :]).all()), "model %d: replicated streams differ" % m
+        y = yb[:, check].cpu().numpy()                               # [T][len(check)]
+        for j, s in enumerate(check):
+            if wl.automate_params:
+                c[ax.CTRL["PARAM1"]], c[ax.CTRL["PARAM2"]] = a1[s], a2[s]
+            yo = orcs[s].run(c, base[s % P, b * T:(b + 1) * T])
+            worst = max(worst, float(np.abs(y[:, j] - yo).max()))
+    assert worst <= 1e-4, worst
+    assert eng.launch_count >= NB
+    eng.close()
