@@ -374,7 +374,11 @@ static int launch_all(aidax_engine* e, cudaStream_t st, int first, int n, int n_
         int ts = n_samples;
         const size_t budget = std::min(e->smem_optin, e->smem_per_sm / (size_t)kv->ctas_per_sm - 1024);
         auto smem_for = [&](int t) { return (size_t)(kv->fixed_smem_floats + kv->NW * kv->warp_smem_floats(t, lp.max_param_tiles)) * sizeof(float); };
-        while (ts > 8 && smem_for(ts) > budget) ts = (ts + 1) / 2;
+        // halving steps with the 3/4 points in between (128, 96, 64, 48, 32, 24, 16, 12, 8): results do not depend on ts
+        while (ts > 8 && smem_for(ts) > budget) {
+            const int three_quarters = (ts * 3 / 4 + 3) & ~3;
+            ts = (three_quarters < ts && three_quarters > (ts + 1) / 2 && ts % 3 != 0) ? three_quarters : (ts % 3 == 0 ? ts * 2 / 3 : (ts + 1) / 2);
+        }
         if (smem_for(ts) > e->smem_optin) return fail(AIDAX_ERR_CAPACITY, "kernel variant needs %zu B shared memory", smem_for(ts));
         const size_t smem = smem_for(ts);
         const void* fn = kv->fn[e->math_mode ? 1 : 0];

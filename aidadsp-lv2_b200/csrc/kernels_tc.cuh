@@ -30,8 +30,31 @@
 #ifndef AIDAX_WHATIF
 #define AIDAX_WHATIF 0
 #endif
+// Which exponentials of the gate epilogue are evaluated on the FMA pipe instead of the XU pipe (bit per site, see
+// TcCell::ope2).  Chosen by measurement on B200.
+#ifndef AIDAX_TC_GROUP
+#define AIDAX_TC_GROUP 2 // 16-column accumulator chunks (4 hidden units each) evaluated per straight-line block
+#endif
+#ifndef AIDAX_SCALED_GATES
+#define AIDAX_SCALED_GATES 0
+#endif
+#ifndef AIDAX_PREFETCH_L2
+#define AIDAX_PREFETCH_L2 1
+#endif
+#ifndef AIDAX_DESC64
+#define AIDAX_DESC64 0 // 1: carry full 64-bit operand descriptors instead of their low words
+#endif
+#ifndef AIDAX_POLY_EX2
+#define AIDAX_POLY_EX2 0
+#endif
 
 namespace aidax {
+
+#if AIDAX_DESC64
+typedef uint64_t tc_desc_t;
+#else
+typedef uint32_t tc_desc_t;
+#endif
 
 template <int H>
 struct TcShape {
@@ -64,10 +87,10 @@ struct TcShape {
 struct TcTile {
     float* a_hi;         // this thread's row in the A operand: a_hi + chunk*512 is a float4 slot
     float* a_lo;
-    uint64_t da_hi;      // shared-memory matrix descriptors of the tile's A (hi, lo) and the CTA's B (hi, lo) at K step 0
-    uint64_t da_lo;
-    uint64_t db_hi;
-    uint64_t db_lo;
+    tc_desc_t da_hi;     // (low words of) the shared-memory matrix descriptors of the tile's A (hi, lo) and the CTA's B (hi, lo)
+    tc_desc_t da_lo;     // at K step 0 (issue_mmas adds the constant high word)
+    tc_desc_t db_hi;
+    tc_desc_t db_lo;
     uint32_t bar_addr;   // the tile's mbarrier
     uint32_t phase;      // its current parity
     uint32_t tmem_d;     // TMEM address of the tile's accumulator (lane 0)
@@ -97,23 +120,33 @@ struct TcCell {
         store_chunk(tt, chunk, make_float2(v0, v1), make_float2(v2, v3));
     }
 
-    // Issued by ONE elected thread of the tile's first warp.  The four base descriptors are warp-uniform values
-    // prepared once per kernel; a K step only adds a constant to the descriptor's address field.
+    // Issued by ONE elected thread of the tile's first warp.  Only the LOW words of the four base descriptors (start
+    // address and leading byte offset) are kept, as opaque loop-invariant values; the high word (stride byte offset +
+    // descriptor version) is a compile-time constant and a K step adds a constant to the low word's address field
+    // (shared memory is < 256 KB, so the 14-bit field cannot carry).  This keeps the per-step uniform-datapath preamble
+    // in front of the first UTCHMMA -- which sits on every stream's critical path -- to a handful of instructions.
     __device__ __forceinline__ static void issue_mmas(const TcTile& tt)
     {
         constexpr uint32_t idesc = tc::make_idesc_tf32(128, S::NMMA);
         constexpr uint32_t LBO_A = 128 * 16, LBO_B = S::N * 16;
+        constexpr uint64_t HI = ((uint64_t)((128u >> 4) & 0x3FFFu) << 32) | (1ull << 46); // SBO = 128 bytes, version 1
+#if AIDAX_DESC64
+        constexpr uint64_t HIW = 0;
+#else
+        constexpr uint64_t HIW = HI;
+#endif
+        const tc_desc_t a_hi = tt.da_hi, a_lo = tt.da_lo, b_hi = tt.db_hi, b_lo = tt.db_lo;
 #pragma unroll
         for (int ks = 0; ks < S::KSTEPS; ++ks) {
-            const uint64_t ao = (ks * 2 * LBO_A) >> 4, bo = (ks * 2 * LBO_B) >> 4;
+            const uint32_t ao = (ks * 2 * LBO_A) >> 4, bo = (ks * 2 * LBO_B) >> 4;
 #pragma unroll
             for (int nh = 0; nh < S::NSPLIT; ++nh) {
                 const uint32_t d = tt.tmem_d + nh * S::NMMA;
-                const uint64_t bn = bo + ((nh * S::NMMA * 16) >> 4);
+                const uint32_t bn = bo + ((nh * S::NMMA * 16) >> 4);
                 // smallest terms first
-                tc::mma_tf32(d, tt.da_lo + ao, tt.db_hi + bn, idesc, ks > 0);
-                tc::mma_tf32(d, tt.da_hi + ao, tt.db_lo + bn, idesc, 1);
-                tc::mma_tf32(d, tt.da_hi + ao, tt.db_hi + bn, idesc, 1);
+                tc::mma_tf32(d, HIW | (a_lo + ao), HIW | (b_hi + bn), idesc, ks > 0);
+                tc::mma_tf32(d, HIW | (a_hi + ao), HIW | (b_lo + bn), idesc, 1);
+                tc::mma_tf32(d, HIW | (a_hi + ao), HIW | (b_hi + bn), idesc, 1);
             }
         }
         tc::mma_commit(tt.bar_addr);
@@ -160,6 +193,51 @@ struct TcCell {
         return tc::add2(make_float2(ex2_approx(e.x), ex2_approx(e.y)), tc::splat2(1.0f));
 #else
         return tc::add2(make_float2(ex2_approx(fminf(e.x, 24.0f)), ex2_approx(fminf(e.y, 24.0f))), tc::splat2(1.0f));
+#endif
+    }
+    // 2^-24 * (1 + 2^e), saturated at 1 (i.e. 2^e clamped at 2^24 - 1; e = +inf from the MUFU saturates as well)
+    __device__ __forceinline__ static float2 scaled_one_plus_exp2(float2 e)
+    {
+        constexpr float s = 5.9604644775390625e-08f;
+#if AIDAX_WHATIF & 2
+        return make_float2(__saturatef(fmaf(e.x, s, s)), __saturatef(fmaf(e.y, s, s)));
+#else
+        return make_float2(__saturatef(fmaf(ex2_approx(e.x), s, s)), __saturatef(fmaf(ex2_approx(e.y), s, s)));
+#endif
+    }
+    // Same value with 2^e evaluated on the FMA pipe instead of the XU pipe: e = n + f, n = round(e), |f| <= 0.5,
+    // 2^f by a degree-6 minimax polynomial (max relative error 0.66 ulp in fp32 Horner form, better than MUFU.EX2's
+    // 2 ulp), 2^n by adding n to the exponent field.  All packed (two hidden units per FADD2/FFMA2).  The kernel is
+    // bound by the XU pipe (8 cycles per warp MUFU) while the FMA pipe idles, so a FRACTION of the exponentials --
+    // chosen by measurement, AIDAX_POLY_EX2 -- is moved over: +11 issue slots, -16 XU cycles per pair.
+    __device__ __forceinline__ static float2 one_plus_exp2_fma(float2 e)
+    {
+        const float2 ec = make_float2(fminf(fmaxf(e.x, -125.0f), 24.0f), fminf(fmaxf(e.y, -125.0f), 24.0f));
+        const float2 magic = tc::splat2(12582912.0f); // 1.5 * 2^23: the sum's low mantissa bits are round(e)
+        const float2 t = tc::add2(ec, magic);
+        const float2 f = tc::sub2(ec, tc::sub2(t, magic));
+        float2 p = tc::splat2(1.534581097e-04f);
+        p = tc::fma2(p, f, tc::splat2(1.339993090e-03f));
+        p = tc::fma2(p, f, tc::splat2(9.618489072e-03f));
+        p = tc::fma2(p, f, tc::splat2(5.550328642e-02f));
+        p = tc::fma2(p, f, tc::splat2(2.402264625e-01f));
+        p = tc::fma2(p, f, tc::splat2(6.931471825e-01f));
+        p = tc::fma2(p, f, tc::splat2(1.0f));
+        // p in [0.707, 1.415], n in [-125, 24]: the exponent field stays normal
+        const float2 r = make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23)),
+                                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23)));
+        return tc::add2(r, tc::splat2(1.0f));
+    }
+    // site: 0 = input/forget/output (LSTM) or update/reset (GRU) gates, 1 = the LSTM candidate gate g,
+    // 2 = tanh of the new cell state (LSTM) / of the candidate (GRU)
+    template <int SITE>
+    __device__ __forceinline__ static float2 ope2(float2 e)
+    {
+#if AIDAX_WHATIF & 2
+        return one_plus_exp2(e);
+#else
+        if constexpr (((AIDAX_POLY_EX2) >> SITE) & 1) return one_plus_exp2_fma(e);
+        else return one_plus_exp2(e);
 #endif
     }
     // In fast-math mode the B operand's columns are pre-scaled so that the accumulator IS that exponent:
@@ -227,7 +305,38 @@ struct TcCell {
         constexpr float L2E = 1.4426950408889634f;
         constexpr int NP = TWO ? 4 : 2; // unit pairs in the group
         const float2 one = tc::splat2(1.0f), m2 = tc::splat2(-2.0f);
-        if (MATH == 0 && CELL == 0) {
+        if (MATH == 0 && CELL == 0 && AIDAX_SCALED_GATES) {
+            // LSTM as below, restated to spend fewer issue slots (the kernel runs at a fixed ~0.46 IPC per scheduler, so
+            // time follows the instruction count).  With a = 1+2^-i, b = 1+2^-f, g = 1+2^(2g), d = 1+2^-o:
+            //   i*tanh(g) = (g-2)/(a g),  f = d/(b d),  o = b/(b d)     -- ONE reciprocal of a*g*b*d, 10 packed ops;
+            // a, g, d and the 1+2^(2c') terms are kept scaled by s = 2^-24 (exact): s*(1+2^e) = sat(fma(2^e, s, s)) -- the
+            // saturation IS the overflow clamp the batched reciprocal needs (one FFMA.SAT instead of FMNMX + FADD), and
+            // the leftover powers of s are folded into constants of FMAs that exist anyway.
+            constexpr float s = 5.9604644775390625e-08f; // 2^-24
+            const float2 s2 = tc::splat2(s), ms2 = tc::splat2(-2.0f * s * s);
+            float2 ogx[NP], ec[NP], t[NP];
+#pragma unroll
+            for (int pr = 0; pr < NP; ++pr) {
+                const uint32_t(&raw)[16] = pr < 2 ? raw0 : raw1;
+                const int j0 = 4 * (pr & 1), u = 4 * q + 2 * pr;
+                const float2 A = scaled_one_plus_exp2(pair(raw, j0)), B = one_plus_exp2(pair(raw, j0 + 1));
+                const float2 G = scaled_one_plus_exp2(pair(raw, j0 + 2)), D = scaled_one_plus_exp2(pair(raw, j0 + 3));
+                const float2 ag = tc::mul2(A, G), bd = tc::mul2(B, D);
+                const float2 r = rcp2(tc::mul2(ag, bd));
+                const float2 rag = tc::mul2(r, bd), rbd = tc::mul2(r, ag); // 1/(s^2 a g), 1/(s b d)
+                const float2 itg = tc::mul2(rag, tc::fma2(s2, G, ms2));    // (g-2)/(a g)
+                const float2 fi = tc::mul2(rbd, D);                         // 1/b
+                ogx[pr] = tc::mul2(rbd, B);                                 // 1/(s d)
+                const float2 c = tc::fma2(fi, make_float2(cst[u], cst[u + 1]), itg);
+                cst[u] = c.x;
+                cst[u + 1] = c.y;
+                ec[pr] = scaled_one_plus_exp2(tc::mul2(c, tc::splat2(2.f * L2E)));
+            }
+            if constexpr (TWO) inv4(ec[0], ec[1], ec[2], ec[3], t[0], t[1], t[2], t[3]);
+            else inv2(ec[0], ec[1], t[0], t[1]);
+#pragma unroll
+            for (int pr = 0; pr < NP; ++pr) hn[pr] = tc::mul2(ogx[pr], tc::fma2(ms2, t[pr], s2)); // (1/d) * (1 - 2/(1+2^(2c')))
+        } else if (MATH == 0 && CELL == 0) {
             // LSTM, RTN/lstm/lstm_xsimd.h:193-213, 271-283: c' = i*tanh(g) + f*c ; h' = o*tanh(c')
             float2 og[NP], ec[NP], t[NP];
 #pragma unroll
@@ -235,12 +344,12 @@ struct TcCell {
                 const uint32_t(&raw)[16] = pr < 2 ? raw0 : raw1;
                 const int j0 = 4 * (pr & 1), u = 4 * q + 2 * pr;
                 float2 ii, fi, gi;
-                inv4(one_plus_exp2(pair(raw, j0)), one_plus_exp2(pair(raw, j0 + 1)), one_plus_exp2(pair(raw, j0 + 2)),
-                     one_plus_exp2(pair(raw, j0 + 3)), ii, fi, gi, og[pr]);
+                inv4(ope2<0>(pair(raw, j0)), ope2<0>(pair(raw, j0 + 1)), ope2<1>(pair(raw, j0 + 2)), ope2<0>(pair(raw, j0 + 3)), ii, fi, gi,
+                     og[pr]);
                 const float2 c = tc::fma2(ii, tc::fma2(m2, gi, one), tc::mul2(fi, make_float2(cst[u], cst[u + 1])));
                 cst[u] = c.x;
                 cst[u + 1] = c.y;
-                ec[pr] = one_plus_exp2(tc::mul2(c, tc::splat2(2.f * L2E)));
+                ec[pr] = ope2<2>(tc::mul2(c, tc::splat2(2.f * L2E)));
             }
             if constexpr (TWO) inv4(ec[0], ec[1], ec[2], ec[3], t[0], t[1], t[2], t[3]);
             else inv2(ec[0], ec[1], t[0], t[1]);
@@ -253,17 +362,21 @@ struct TcCell {
             for (int c4 = 0; c4 < NP / 2; ++c4) {
                 const uint32_t(&raw)[16] = c4 == 0 ? raw0 : raw1;
                 float2 r0, r1;
-                inv4(one_plus_exp2(pair(raw, 0)), one_plus_exp2(pair(raw, 1)), one_plus_exp2(pair(raw, 4)), one_plus_exp2(pair(raw, 5)),
-                     z[2 * c4], r0, z[2 * c4 + 1], r1);
-                e[2 * c4] = one_plus_exp2(tc::fma2(r0, pair(raw, 2), pair(raw, 3)));
-                e[2 * c4 + 1] = one_plus_exp2(tc::fma2(r1, pair(raw, 6), pair(raw, 7)));
+                inv4(ope2<0>(pair(raw, 0)), ope2<0>(pair(raw, 1)), ope2<0>(pair(raw, 4)), ope2<0>(pair(raw, 5)), z[2 * c4], r0, z[2 * c4 + 1], r1);
+                if constexpr (AIDAX_SCALED_GATES) { // the candidate's 1+2^e scaled by 2^-24, see the LSTM branch
+                    e[2 * c4] = scaled_one_plus_exp2(tc::fma2(r0, pair(raw, 2), pair(raw, 3)));
+                    e[2 * c4 + 1] = scaled_one_plus_exp2(tc::fma2(r1, pair(raw, 6), pair(raw, 7)));
+                } else {
+                    e[2 * c4] = ope2<2>(tc::fma2(r0, pair(raw, 2), pair(raw, 3)));
+                    e[2 * c4 + 1] = ope2<2>(tc::fma2(r1, pair(raw, 6), pair(raw, 7)));
+                }
             }
             if constexpr (TWO) inv4(e[0], e[1], e[2], e[3], t[0], t[1], t[2], t[3]);
             else inv2(e[0], e[1], t[0], t[1]);
 #pragma unroll
             for (int pr = 0; pr < NP; ++pr) {
                 const int u = 4 * q + 2 * pr;
-                const float2 hh = tc::fma2(m2, t[pr], one);
+                const float2 hh = tc::fma2(AIDAX_SCALED_GATES ? tc::splat2(-2.0f * 5.9604644775390625e-08f) : m2, t[pr], one);
                 hn[pr] = tc::fma2(tc::sub2(one, z[pr]), hh, tc::mul2(z[pr], make_float2(cst[u], cst[u + 1])));
                 cst[u] = hn[pr].x;
                 cst[u + 1] = hn[pr].y;
@@ -330,9 +443,9 @@ struct TcCell {
             // straight-line block, so the 8 + 2 batched reciprocal chains of a group overlap each other's MUFU latency
             float2 y2 = make_float2(db, 0.f);
 #pragma unroll
-            for (int q = 0; q < H / 4; q += 2) {
+            for (int q = 0; q < H / 4; q += AIDAX_TC_GROUP) {
                 constexpr int NQ = H / 4;
-                const bool two = q + 1 < NQ;
+                const bool two = AIDAX_TC_GROUP == 2 && q + 1 < NQ;
                 uint32_t raw0[16], raw1[16];
                 tc::tmem_ld16(tt.tmem_ld + 16 * q, raw0);
                 if (two) tc::tmem_ld16(tt.tmem_ld + 16 * (q + 1), raw1);
@@ -394,6 +507,30 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
     const int input_size = md.input_size;
     const int n_ptiles = input_size - 1;
 
+#if AIDAX_PREFETCH_L2
+    // ---- the warp's whole input period goes to L2 now (a few prefetch instructions per lane), so that the tile
+    // loads of the sub-block loop below find it there instead of waiting on HBM with nothing else to issue
+    // (ncu source view: 7 % of all warp samples sat on those loads' scoreboard)
+    {
+        const int pslot = p.blk_slots[(size_t)blk * CS + warp * 32 + lane];
+        if (p.layout == 0) { // planar [stream][n]: each lane owns its stream's row
+            if (pslot >= 0) {
+                const float* src = p.in + (size_t)(pslot - p.first_stream) * p.stride;
+                for (int t = 0; t < p.n_samples; t += 32) tc::prefetch_l2(src + t);
+            }
+        } else { // interleaved [n][stream]: one 128-byte segment per sample row for the warp; lane l takes rows l, l+32, ...
+            const int s0 = __shfl_sync(0xffffffffu, pslot, 0);
+            if (s0 >= 0) {
+                const float* src = p.in + (s0 - p.first_stream);
+                for (int t = lane; t < p.n_samples; t += 32) {
+                    tc::prefetch_l2(src + (size_t)t * p.stride);
+                    tc::prefetch_l2(src + (size_t)t * p.stride + 31); // the segment may straddle two lines
+                }
+            }
+        }
+    }
+#endif
+
     // ---- B operand (hi, lo) from the packed weight block (layout.h): B[n = column_of(unit, gate)][k]
     {
         const float* wk = md.weights;
@@ -433,10 +570,10 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
     {
         constexpr uint32_t LBO_A = 128 * 16, LBO_B = S::N * 16, SBO = 128;
         const uint32_t a_addr = tc::smem_u32(Abase + tile * 2 * S::A_FLOATS);
-        tt.da_hi = tc::make_smem_desc(a_addr, LBO_A, SBO);
-        tt.da_lo = tc::make_smem_desc(a_addr + S::A_FLOATS * 4, LBO_A, SBO);
-        tt.db_hi = tc::make_smem_desc(tc::smem_u32(Bh), LBO_B, SBO);
-        tt.db_lo = tc::make_smem_desc(tc::smem_u32(Bl), LBO_B, SBO);
+        tt.da_hi = (tc_desc_t)tc::make_smem_desc(a_addr, LBO_A, SBO);
+        tt.da_lo = (tc_desc_t)tc::make_smem_desc(a_addr + S::A_FLOATS * 4, LBO_A, SBO);
+        tt.db_hi = (tc_desc_t)tc::make_smem_desc(tc::smem_u32(Bh), LBO_B, SBO);
+        tt.db_lo = (tc_desc_t)tc::make_smem_desc(tc::smem_u32(Bl), LBO_B, SBO);
     }
     tt.bar_addr = tc::smem_u32(&bars[tile]);
     tt.phase = 0;

@@ -35,6 +35,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar_addr, uint32_t parity)
     while (!mbar_try_wait(bar_addr, parity)) {}
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* gptr)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(gptr)));
+}
+
 // ---- fences
 // generic-proxy shared-memory writes -> visible to the async proxy (the tensor core reads operands through it)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

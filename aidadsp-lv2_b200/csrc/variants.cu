@@ -30,6 +30,15 @@ static int wsf_tc(int ts, int np) { return TcShape<H>::warp_floats(ts, np); }
       &wsf_tc<Hh>, 1, (TcShape<Hh>::fixed_floats(NTt) + 3) & ~3, RES }
 #define BOTH_TC(Hh, NTt, RES) VT(0, Hh, NTt, RES), VT(1, Hh, NTt, RES)
 
+#ifndef AIDAX_TC_NT32
+#define AIDAX_TC_NT32 3
+#endif
+#ifndef AIDAX_TC_NT40
+#define AIDAX_TC_NT40 2
+#endif
+#ifndef AIDAX_TC_RES16
+#define AIDAX_TC_RES16 4
+#endif
 #define CAT_(a, b) a##b
 #define CAT(a, b) CAT_(a, b)
 
@@ -41,15 +50,15 @@ const KernelVariant CAT(kVariantsH, AIDAX_VARIANT_H)[] = {
 #elif AIDAX_VARIANT_H == 12
     BOTH(12, 4, 1, 4), BOTH(12, 4, 2, 4), BOTH(12, 4, 4, 4), BOTH_TC(12, 1, 4),
 #elif AIDAX_VARIANT_H == 16
-    BOTH(16, 16, 1, 4), BOTH(16, 16, 4, 4), BOTH(16, 8, 8, 4), BOTH_TC(16, 1, 4),
+    BOTH(16, 16, 1, 4), BOTH(16, 16, 4, 4), BOTH(16, 8, 8, 4), BOTH_TC(16, 1, AIDAX_TC_RES16),
 #elif AIDAX_VARIANT_H == 20
     BOTH(20, 4, 1, 4), BOTH(20, 4, 2, 4), BOTH(20, 4, 4, 4), BOTH_TC(20, 1, 3),
 #elif AIDAX_VARIANT_H == 24
     BOTH(24, 8, 1, 4), BOTH(24, 8, 4, 4), BOTH(24, 8, 8, 4), BOTH_TC(24, 1, 3),
 #elif AIDAX_VARIANT_H == 32
-    BOTH(32, 32, 1, 4), BOTH(32, 16, 4, 4), BOTH(32, 8, 4, 4), BOTH_TC(32, 2, 1),
+    BOTH(32, 32, 1, 4), BOTH(32, 16, 4, 4), BOTH(32, 8, 4, 4), BOTH_TC(32, AIDAX_TC_NT32, 1),
 #elif AIDAX_VARIANT_H == 40
-    BOTH(40, 8, 1, 4), BOTH(40, 8, 2, 4), BOTH(40, 8, 4, 4), BOTH_TC(40, 2, 1),
+    BOTH(40, 8, 1, 4), BOTH(40, 8, 2, 4), BOTH(40, 8, 4, 4), BOTH_TC(40, AIDAX_TC_NT40, 1),
 #elif AIDAX_VARIANT_H == 64
     BOTH(64, 32, 1, 4), BOTH(64, 32, 4, 4), BOTH(64, 16, 4, 4),
 #elif AIDAX_VARIANT_H == 80
