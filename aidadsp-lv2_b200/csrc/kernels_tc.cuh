@@ -36,10 +36,16 @@
 #define AIDAX_TC_GROUP 2 // 16-column accumulator chunks (4 hidden units each) evaluated per straight-line block
 #endif
 #ifndef AIDAX_SCALED_GATES
-#define AIDAX_SCALED_GATES 0
+#define AIDAX_SCALED_GATES 1
 #endif
 #ifndef AIDAX_PREFETCH_L2
 #define AIDAX_PREFETCH_L2 1
+#endif
+#ifndef AIDAX_B_RN
+#define AIDAX_B_RN 1 // weights: hi part of the tf32 split rounded to nearest (free: B is built once per CTA)
+#endif
+#ifndef AIDAX_A_RN
+#define AIDAX_A_RN 0 // recurrent vector: same (one more integer add per element and step)
 #endif
 #ifndef AIDAX_DESC64
 #define AIDAX_DESC64 0 // 1: carry full 64-bit operand descriptors instead of their low words
@@ -107,8 +113,13 @@ struct TcCell {
     __device__ __forceinline__ static void store_chunk(const TcTile& tt, int chunk, float2 v01, float2 v23)
     {
         // 3xTF32 split (tc::split_tf32) of four values, the subtraction packed
-        const float2 h01 = make_float2(__uint_as_float(__float_as_uint(v01.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v01.y) & 0xFFFFE000u));
-        const float2 h23 = make_float2(__uint_as_float(__float_as_uint(v23.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v23.y) & 0xFFFFE000u));
+#if AIDAX_A_RN
+        constexpr uint32_t RB = 0x1000u; // hi rounded to nearest (see tc::split_tf32_rn)
+#else
+        constexpr uint32_t RB = 0u;
+#endif
+        const float2 h01 = make_float2(__uint_as_float((__float_as_uint(v01.x) + RB) & 0xFFFFE000u), __uint_as_float((__float_as_uint(v01.y) + RB) & 0xFFFFE000u));
+        const float2 h23 = make_float2(__uint_as_float((__float_as_uint(v23.x) + RB) & 0xFFFFE000u), __uint_as_float((__float_as_uint(v23.y) + RB) & 0xFFFFE000u));
         const float2 d01 = tc::sub2(v01, h01), d23 = tc::sub2(v23, h23);
         *reinterpret_cast<float4*>(tt.a_hi + chunk * 512) = make_float4(h01.x, h01.y, h23.x, h23.y);
         *reinterpret_cast<float4*>(tt.a_lo + chunk * 512) =
@@ -543,7 +554,11 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
             else if (k == H + 3) w = __ldg(bias + src);
             if (MATH == 0) w *= Cell::column_scale(g); // the accumulator is directly the exponent of 2 the gate needs
             float hi, lo;
+#if AIDAX_B_RN
+            tc::split_tf32_rn(w, hi, lo);
+#else
             tc::split_tf32(w, hi, lo);
+#endif
             const int off = (k >> 2) * (S::N * 4) + n * 4 + (k & 3);
             Bh[off] = hi;
             Bl[off] = lo;

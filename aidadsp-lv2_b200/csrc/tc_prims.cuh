@@ -144,6 +144,15 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo)
     hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
     lo = __uint_as_float(__float_as_uint(x - hi) + 0x1000u);
 }
+// Same with hi ROUNDED to the nearest tf32 value: lo is then signed and at most half a tf32 ulp, so the dropped
+// lo.lo term of the 3-product scheme is half as large and has no systematic sign (with both operands truncated
+// it always has the sign of the exact product).  One more integer add per element: used where the split is built
+// once (the weights), while the per-step split of the recurrent vector stays truncating.
+__device__ __forceinline__ void split_tf32_rn(float x, float& hi, float& lo)
+{
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    lo = __uint_as_float(__float_as_uint(x - hi) + 0x1000u);
+}
 
 // ---- packed fp32 pairs (sm_100 FMUL2 / FADD2 / FFMA2): two IEEE round-to-nearest operations per issue slot.
 // The gate epilogue is bound by issue slots and the XU pipe, not by FMA-pipe throughput, so its fp32 arithmetic
