@@ -261,6 +261,17 @@ __device__ __forceinline__ void load_tile(float* xbuf, const RenderParams& p, co
             for (int i = 0; i < 8; ++i)
                 if (t + i < ts) xbuf[(t + i) * XP + lane] = v[i];
         }
+    } else if constexpr (WS == 1) { // interleaved [n][stream], one stream per warp: a lane's loads all in flight before the first store
+        const int slot = wslots[0];
+        const float* src = p.in + (size_t)t0 * p.stride + (slot - p.first_stream);
+        for (int t = lane; t < ts; t += 128) {
+            float v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = (slot >= 0 && t + 32 * i < ts) ? __ldg(src + (size_t)(t + 32 * i) * p.stride) : 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (t + 32 * i < ts) xbuf[(t + 32 * i) * XP] = v[i];
+        }
     } else { // interleaved [n][stream]
         for (int idx = lane; idx < ts * WS; idx += 32) {
             const int t = idx / WS, j = idx - t * WS;

@@ -4,6 +4,7 @@
 // (register tile of S streams x 4U gate rows per lane, >= 10 FFMA per 128-bit shared load).
 #include "kernels.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_w.cuh"
 #include "variants.h"
 
 #ifndef AIDAX_VARIANT_H
@@ -39,6 +40,14 @@ static int wsf_tc(int ts, int np) { return TcShape<H>::warp_floats(ts, np); }
 #ifndef AIDAX_TC_RES16
 #define AIDAX_TC_RES16 4
 #endif
+// warp-per-stream latency variants (kernels_w.cuh): one stream per warp, hidden size <= 16
+static int wsf_w(int ts, int np) { return WShape::warp_floats(ts, np); }
+#define VW(CELL, Hh, NWw)                                                                                \
+    { CELL, Hh, 32, 1, NWw, 1,                                                                           \
+      { (const void*)&chain_kernel_w<CELL, Hh, NWw, 0>, (const void*)&chain_kernel_w<CELL, Hh, NWw, 1> }, \
+      &wsf_w, 0, 0, 2 }
+#define BOTH_W(Hh, NWw) VW(0, Hh, NWw), VW(1, Hh, NWw)
+
 #define CAT_(a, b) a##b
 #define CAT(a, b) CAT_(a, b)
 
@@ -46,11 +55,11 @@ const KernelVariant CAT(kVariantsH, AIDAX_VARIANT_H)[] = {
 #if AIDAX_VARIANT_H == 0
     V(2, 8, 8, 8, 4),
 #elif AIDAX_VARIANT_H == 8
-    BOTH(8, 8, 1, 4), BOTH(8, 8, 4, 4), BOTH(8, 8, 8, 4), BOTH_TC(8, 1, 4),
+    BOTH_W(8, 4), BOTH(8, 8, 1, 4), BOTH(8, 8, 4, 4), BOTH(8, 8, 8, 4), BOTH_TC(8, 1, 4),
 #elif AIDAX_VARIANT_H == 12
-    BOTH(12, 4, 1, 4), BOTH(12, 4, 2, 4), BOTH(12, 4, 4, 4), BOTH_TC(12, 1, 4),
+    BOTH_W(12, 4), BOTH(12, 4, 1, 4), BOTH(12, 4, 2, 4), BOTH(12, 4, 4, 4), BOTH_TC(12, 1, 4),
 #elif AIDAX_VARIANT_H == 16
-    BOTH(16, 16, 1, 4), BOTH(16, 16, 4, 4), BOTH(16, 8, 8, 4), BOTH_TC(16, 1, AIDAX_TC_RES16),
+    BOTH_W(16, 4), BOTH(16, 16, 1, 4), BOTH(16, 16, 4, 4), BOTH(16, 8, 8, 4), BOTH_TC(16, 1, AIDAX_TC_RES16),
 #elif AIDAX_VARIANT_H == 20
     BOTH(20, 4, 1, 4), BOTH(20, 4, 2, 4), BOTH(20, 4, 4, 4), BOTH_TC(20, 1, 3),
 #elif AIDAX_VARIANT_H == 24
