@@ -32,41 +32,62 @@ struct WShape {
     }
 };
 
-// One pass of a systolic biquad cascade over x[0..ts): lane j < NST runs stage j on sample i-j in iteration i.
+// One pass of a systolic biquad cascade over x[0..ts): lane j < NST runs stage j on sample i - 2j in iteration i.
 //   f / bq_on : this lane's biquad (already loaded) and whether it is active (inactive = pass-through)
 //   gain_on   : this lane multiplies its output by the exponential smoother (mem, coef, tgt) -- the pre-gain ramp of
 //               stage 0 in the pre pass, the master ramp of the last stage in the post pass
+// Neighbouring stages are skewed by TWO iterations: a stage's output is shuffled up in the iteration after it was
+// produced and consumed in the one after that, so the shuffle and the float<->double conversions of one sample overlap
+// the arithmetic of the next and an iteration costs about one biquad state recurrence, not the whole
+// shuffle -> convert -> multiply-add -> convert chain.  The bulk of the pass (every stage in range) runs without
+// range checks; the pipeline fill and drain use the checked body.
+template <bool CHECKED, int NST>
+__device__ __forceinline__ void systolic_step(float* x, int ts, int i, int& t, unsigned tsu, int lane, BiquadReg& f, bool bq_on, bool gain_on,
+                                              float& mem, float coef, float tgt, float& out, float& recv)
+{
+    const float tmp = __shfl_up_sync(0xffffffffu, out, 1);
+    const float vin = lane == 0 ? x[CHECKED ? min(i, ts - 1) : i] : recv;
+    // Biquad::process (common/Biquad.h:53-58), as BiquadReg::process
+    const double xd = (double)vin;
+    const double o = __dadd_rn(__dmul_rn(xd, f.a0), f.z1);
+    const double z1n = __dsub_rn(__dadd_rn(__dmul_rn(xd, f.a1), f.z2), __dmul_rn(f.b1, o));
+    const double z2n = __dsub_rn(__dmul_rn(xd, f.a2), __dmul_rn(f.b2, o));
+    float v = bq_on ? __double2float_rn(o) : vin;
+    // ExponentialValueSmoother::next + applyGainRamp (rt-neural-generic.cpp:34-38)
+    const float g = __fadd_rn(__fmul_rn(mem, coef), tgt);
+    v = gain_on ? __fmul_rn(v, g) : v;
+    if (CHECKED) {
+        const bool act = (unsigned)t < tsu;
+        f.z1 = act ? z1n : f.z1;
+        f.z2 = act ? z2n : f.z2;
+        mem = (act && gain_on) ? g : mem;
+        out = act ? v : out;
+        if (act && lane == NST - 1) x[t] = v;
+    } else {
+        // stages that are off (or lanes beyond the cascade) carry state nobody stores
+        f.z1 = z1n;
+        f.z2 = z2n;
+        mem = gain_on ? g : mem;
+        out = v;
+        if (lane == NST - 1) x[t] = v;
+    }
+    recv = tmp;
+    ++t;
+}
+
 template <int NST>
 __device__ __forceinline__ void systolic_pass(float* x, int ts, int lane, BiquadReg& f, bool bq_on, bool gain_on, float& mem, float coef,
                                               float tgt)
 {
-    // Branch-free body (selects instead of divergent branches: a lone warp has nobody to hide a branch's latency
-    // behind): every lane evaluates its stage every iteration, state and output only move when the lane is in range.
-    float out = 0.f;
-    const bool staged = lane < NST;
+    constexpr int LAG = 2 * (NST - 1);
+    const unsigned tsu = lane < NST ? (unsigned)ts : 0u;
+    float out = 0.f, recv = 0.f;
+    int t = -2 * lane;
+    int i = 0;
+    for (; i < min(LAG, ts + LAG); ++i) systolic_step<true, NST>(x, ts, i, t, tsu, lane, f, bq_on, gain_on, mem, coef, tgt, out, recv);
 #pragma unroll 2
-    for (int i = 0; i < ts + NST - 1; ++i) {
-        const float up = __shfl_up_sync(0xffffffffu, out, 1);
-        const int t = i - lane;
-        const bool act = staged && t >= 0 && t < ts;
-        const float vin = lane == 0 ? x[min(i, ts - 1)] : up;
-        // Biquad::process (common/Biquad.h:53-58), as BiquadReg::process
-        const double xd = (double)vin;
-        const double o = __dadd_rn(__dmul_rn(xd, f.a0), f.z1);
-        const double z1n = __dsub_rn(__dadd_rn(__dmul_rn(xd, f.a1), f.z2), __dmul_rn(f.b1, o));
-        const double z2n = __dsub_rn(__dmul_rn(xd, f.a2), __dmul_rn(f.b2, o));
-        const bool upd = act && bq_on;
-        f.z1 = upd ? z1n : f.z1;
-        f.z2 = upd ? z2n : f.z2;
-        float v = bq_on ? __double2float_rn(o) : vin;
-        // ExponentialValueSmoother::next + applyGainRamp (rt-neural-generic.cpp:34-38)
-        const float g = __fadd_rn(__fmul_rn(mem, coef), tgt);
-        const bool gupd = act && gain_on;
-        mem = gupd ? g : mem;
-        v = gain_on ? __fmul_rn(v, g) : v;
-        out = act ? v : out;
-        if (act && lane == NST - 1) x[t] = v;
-    }
+    for (; i < ts; ++i) systolic_step<false, NST>(x, ts, i, t, tsu, lane, f, bq_on, gain_on, mem, coef, tgt, out, recv);
+    for (; i < ts + LAG; ++i) systolic_step<true, NST>(x, ts, i, t, tsu, lane, f, bq_on, gain_on, mem, coef, tgt, out, recv);
 }
 
 template <int CELL, int H, int MATH>
@@ -124,32 +145,24 @@ struct TileW {
 
         int cur = 0;
         float hlast = 0.f, yprev = 0.f, xgprev = 0.f;
-        for (int t = 0; t <= n; ++t) {
-            // Dense of the PREVIOUS step: a shuffle butterfly over the owner lanes (odd lanes and padding units carry
-            // 0).  Deferred by one step so that its four dependent shuffles fill the wait for this step's h loads
-            // and FFMA chains instead of sitting on the recurrence's critical path.
-            if (t > 0) {
-                float y = yprev;
-                y += __shfl_xor_sync(0xffffffffu, y, 2);
-                y += __shfl_xor_sync(0xffffffffu, y, 4);
-                y += __shfl_xor_sync(0xffffffffu, y, 8);
-                y += __shfl_xor_sync(0xffffffffu, y, 16);
-                if (x && commit && lane == 0) x[t - 1] = (in_skip ? xgprev + (y + db) : (y + db)) * out_gain;
-                if (t == n) break;
-            } else if (n == 0) {
-                break;
-            }
+        const float* xs = x ? x : hbuf; const int xstep = x ? 1 : 0;
+        const float* p1s = p1 ? p1 : hbuf; const int p1step = p1 ? 1 : 0;
+        const float* p2s = p2 ? p2 : hbuf; const int p2step = p2 ? 1 : 0;
+        for (int t = 0; t < n; ++t) {
             const float* hc = hbuf + cur * HP;
             float hv[HP];
             lds_vec<HP>(hv, hc);
-            const float xg = x ? x[t] * in_gain : 0.f;
-            const float v1 = p1 ? p1[t] : p1c, v2 = p2 ? p2[t] : p2c;
+            // branch-free operand fetch (the time loop is one basic block): absent tiles read a valid dummy address
+            const float xr = xs[t * xstep], p1r = p1s[t * p1step], p2r = p2s[t * p2step];
+            const float xg = x ? xr * in_gain : 0.f;
+            const float v1 = p1 ? p1r : p1c, v2 = p2 ? p2r : p2c;
 
-            // two gate rows, two partial sums each (four independent FFMA chains)
+            // two gate rows, two partial sums each (four independent FFMA chains); the weight rows of inputs the
+            // model does not have are zero in the packed block
             float a0 = w0[HP + kMaxInput], a1 = w1[HP + kMaxInput];
             float b0 = w0[HP] * xg, b1 = w1[HP] * xg;
-            if (input_size >= 2) { a0 = fmaf(w0[HP + 1], v1, a0); a1 = fmaf(w1[HP + 1], v1, a1); }
-            if (input_size >= 3) { b0 = fmaf(w0[HP + 2], v2, b0); b1 = fmaf(w1[HP + 2], v2, b1); }
+            a0 = fmaf(w0[HP + 1], v1, a0); a1 = fmaf(w1[HP + 1], v1, a1);
+            b0 = fmaf(w0[HP + 2], v2, b0); b1 = fmaf(w1[HP + 2], v2, b1);
 #pragma unroll
             for (int k = 0; k < H; k += 2) {
                 a0 = fmaf(w0[k], hv[k], a0);
@@ -159,6 +172,18 @@ struct TileW {
             }
             a0 += b0;
             a1 += b1;
+
+            // Dense of the PREVIOUS step: a shuffle butterfly over the owner lanes (odd lanes and padding units carry
+            // 0).  Deferred by one step and kept in the same straight-line block as the FFMA chains above, so its four
+            // dependent shuffles are scheduled into their shadow instead of sitting on the recurrence's critical path.
+            {
+                float y = yprev;
+                y += __shfl_xor_sync(0xffffffffu, y, 2);
+                y += __shfl_xor_sync(0xffffffffu, y, 4);
+                y += __shfl_xor_sync(0xffffffffu, y, 8);
+                y += __shfl_xor_sync(0xffffffffu, y, 16);
+                if (x && commit && lane == 0 && t > 0) x[t - 1] = (in_skip ? xgprev + (y + db) : (y + db)) * out_gain;
+            }
 
             float hnew;
             if (CELL == 0) {
@@ -185,6 +210,14 @@ struct TileW {
             xgprev = xg;
             __syncwarp();
             cur ^= 1;
+        }
+        if (n > 0) { // Dense of the last step
+            float y = yprev;
+            y += __shfl_xor_sync(0xffffffffu, y, 2);
+            y += __shfl_xor_sync(0xffffffffu, y, 4);
+            y += __shfl_xor_sync(0xffffffffu, y, 8);
+            y += __shfl_xor_sync(0xffffffffu, y, 16);
+            if (x && commit && lane == 0) x[n - 1] = (in_skip ? xgprev + (y + db) : (y + db)) * out_gain;
         }
         __syncwarp();
 

@@ -45,7 +45,7 @@ static int wsf_w(int ts, int np) { return WShape::warp_floats(ts, np); }
 #define VW(CELL, Hh, NWw)                                                                                \
     { CELL, Hh, 32, 1, NWw, 1,                                                                           \
       { (const void*)&chain_kernel_w<CELL, Hh, NWw, 0>, (const void*)&chain_kernel_w<CELL, Hh, NWw, 1> }, \
-      &wsf_w, 0, 0, 2 }
+      &wsf_w, 2, 0, 2 }
 #define BOTH_W(Hh, NWw) VW(0, Hh, NWw), VW(1, Hh, NWw)
 
 #define CAT_(a, b) a##b

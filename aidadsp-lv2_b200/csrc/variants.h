@@ -11,7 +11,8 @@ struct KernelVariant {
     int ws;     // streams per warp
     const void* fn[2]; // [math_mode] kernel entry (for cudaFuncSetAttribute / cudaLaunchKernel)
     int (*warp_smem_floats)(int ts, int n_param_tiles);
-    int kind;             // 0 = FP32 register-tiled recurrence (kernels.cuh), 1 = tcgen05 tensor-core recurrence (kernels_tc.cuh)
+    int kind;             // 0 = FP32 register-tiled recurrence (kernels.cuh), 1 = tcgen05 tensor-core recurrence (kernels_tc.cuh),
+                          // 2 = FP32 warp-per-stream latency shape (kernels_w.cuh)
     int fixed_smem_floats; // shared memory that does not scale with the sub-block length (weights / MMA operands)
     int ctas_per_sm;      // residency the shared-memory budget is sized for
 };
