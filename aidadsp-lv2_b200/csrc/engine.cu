@@ -279,13 +279,14 @@ static int upload_dirty(aidax_engine* e, int first, int n, cudaStream_t st)
 static const KernelVariant* choose_variant(const aidax_engine* e, const Family& fam, int n_streams)
 {
     const auto& v = fam.variants;
+    // auto: small batches take the warp-per-stream shape while it is the fastest (measured on B200, LSTM-16: 76 vs 113 us
+    // per period at 2048 streams, 129 vs 207 us at 4096 -- register-tiled and tensor-core shape alike --, 234 vs 207 us
+    // at 8192) ...
+    if (e->tile_mode == 0 && !v.empty() && v.front()->kind == 2 && n_streams <= e->sm_count * 40) return v.front();
     if (fam.tc && (e->tile_mode == 3 || (e->tile_mode == 0 && n_streams >= e->tc_min_streams))) return fam.tc;
     if (v.size() == 1) return v[0];
     if (e->tile_mode == 1) return v.front();
     if (e->tile_mode == 2) return v.back();
-    // auto: small batches take the warp-per-stream shape while it is the fastest (measured on B200, LSTM-16: 76 vs 113 us
-    // per period at 2048 streams, 129 vs 207 us at 4096, 234 vs 207 us at 8192) ...
-    if (v.front()->kind == 2 && n_streams <= e->sm_count * 40) return v.front();
     // ... otherwise the widest tile that still gives every SM at least 4 warps; failing that trade FFMA
     // efficiency for parallelism (fewer streams per warp).
     const int want_warps = e->sm_count * 4;

@@ -30,8 +30,8 @@
 #ifndef AIDAX_WHATIF
 #define AIDAX_WHATIF 0
 #endif
-// Which exponentials of the gate epilogue are evaluated on the FMA pipe instead of the XU pipe (bit per site, see
-// TcCell::ope2).  Chosen by measurement on B200.
+// Build-time choices of the tensor-core kernel, each settled by measurement on B200 (tools/variant.sh builds scratch
+// libraries with other values, tools/variant_run.py / tools/acc_run.py time and check them; DESIGN.md 3.2 has the table).
 #ifndef AIDAX_TC_GROUP
 #define AIDAX_TC_GROUP 2 // 16-column accumulator chunks (4 hidden units each) evaluated per straight-line block
 #endif
@@ -50,6 +50,8 @@
 #ifndef AIDAX_DESC64
 #define AIDAX_DESC64 0 // 1: carry full 64-bit operand descriptors instead of their low words
 #endif
+// Which exponentials of the gate epilogue are evaluated on the FMA pipe instead of the XU pipe (bit per site, see
+// TcCell::ope2): measured slower for H = 16 (+2 % with the tanh(c') site alone, +30 % with all), so none.
 #ifndef AIDAX_POLY_EX2
 #define AIDAX_POLY_EX2 0
 #endif
@@ -518,29 +520,6 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
     const int input_size = md.input_size;
     const int n_ptiles = input_size - 1;
 
-#if AIDAX_PREFETCH_L2
-    // ---- the warp's whole input period goes to L2 now (a few prefetch instructions per lane), so that the tile
-    // loads of the sub-block loop below find it there instead of waiting on HBM with nothing else to issue
-    // (ncu source view: 7 % of all warp samples sat on those loads' scoreboard)
-    {
-        const int pslot = p.blk_slots[(size_t)blk * CS + warp * 32 + lane];
-        if (p.layout == 0) { // planar [stream][n]: each lane owns its stream's row
-            if (pslot >= 0) {
-                const float* src = p.in + (size_t)(pslot - p.first_stream) * p.stride;
-                for (int t = 0; t < p.n_samples; t += 32) tc::prefetch_l2(src + t);
-            }
-        } else { // interleaved [n][stream]: one 128-byte segment per sample row for the warp; lane l takes rows l, l+32, ...
-            const int s0 = __shfl_sync(0xffffffffu, pslot, 0);
-            if (s0 >= 0) {
-                const float* src = p.in + (s0 - p.first_stream);
-                for (int t = lane; t < p.n_samples; t += 32) {
-                    tc::prefetch_l2(src + (size_t)t * p.stride);
-                    tc::prefetch_l2(src + (size_t)t * p.stride + 31); // the segment may straddle two lines
-                }
-            }
-        }
-    }
-#endif
 
     // ---- B operand (hi, lo) from the packed weight block (layout.h): B[n = column_of(unit, gate)][k]
     {
@@ -636,6 +615,27 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
     for (int t0 = 0; t0 < p.n_samples; t0 += p.ts) {
         const int ts = min(p.ts, p.n_samples - t0);
         load_tile<32, XP>(xbuf, p, wslots, t0, ts, lane);
+#if AIDAX_PREFETCH_L2
+        // the NEXT sub-block's rows go to L2 while this one is filtered and run through the network, so that its tile
+        // load does not wait on HBM with nothing else to issue (ncu source view: 7 % of all warp samples sat on those
+        // loads' scoreboard).  One sub-block ahead only: prefetching the whole period up front cost 25 % more DRAM reads
+        // (lines evicted before use) for no extra gain.
+        if (t0 + ts < p.n_samples) {
+            const int tn = t0 + ts, nn = min(p.ts, p.n_samples - tn);
+            if (p.layout == 0) { // planar [stream][n]: each lane owns its stream's row
+                if (cslot >= 0) {
+                    const float* src = p.in + (size_t)(cslot - p.first_stream) * p.stride + tn;
+                    for (int t = 0; t < nn; t += 32) tc::prefetch_l2(src + t);
+                }
+            } else { // interleaved [n][stream]: one 128-byte segment per sample row for the warp; lane l takes rows l, l+32, ...
+                const int s0 = wslots[0];
+                if (s0 >= 0) {
+                    const float* src = p.in + (size_t)tn * p.stride + (s0 - p.first_stream);
+                    for (int t = lane; t < nn; t += 32) tc::prefetch_l2(src + (size_t)t * p.stride);
+                }
+            }
+        }
+#endif
         __syncwarp();
 
         // ---- stages before the network (run(), rt-neural-generic.cpp:622-644)

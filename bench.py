@@ -185,7 +185,7 @@ def kernel_name(wl, n_local, tile_mode):
     m = wl.models[0]
     tc = m.hidden <= 40 and (tile_mode == 3 or (tile_mode == 0 and n_local >= 4096))
     return ("chain_kernel_tc (fused chain + tcgen05 3xTF32 gate GEMM in TMEM, thread-per-stream gate epilogue)" if tc
-            else "chain_kernel (fused chain + FP32 register-tiled recurrence)"), tc
+            else "chain_kernel_w / chain_kernel (fused chain + FP32 recurrence: warp-per-stream latency shape for small batches, register-tiled shapes above)"), tc
 
 
 def run_ours(args, rank, world, local_rank):

@@ -25,4 +25,18 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:chai
 echo "ncu full exit $?"
 ncu -i $OUT/${TAG}_tc16_full.ncu-rep --page details > $OUT/${TAG}_ncu_tc16_details.txt 2>&1
 ncu -i $OUT/${TAG}_tc16_full.ncu-rep --page raw --csv > $OUT/${TAG}_ncu_tc16_raw.csv 2>&1
-grep -E "dram__bytes_(read|write).sum\"" $OUT/${TAG}_ncu_tc16_raw.csv | head
+python - "$OUT/${TAG}_ncu_tc16_raw.csv" <<'PY'
+import csv, sys
+rows = list(csv.reader(open(sys.argv[1])))
+hdr = rows[0]
+for name in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"):
+    if name in hdr:
+        print(name, [r[hdr.index(name)] for r in rows[1:3]])
+PY
+echo "== per-shape tables"
+timeout 200 python tools/quick_bench_tc.py > $OUT/${TAG}_tc_shapes.txt 2>&1; tail -12 $OUT/${TAG}_tc_shapes.txt
+timeout 200 python tools/quick_bench_lat.py > $OUT/${TAG}_latency_shapes.txt 2>&1; tail -20 $OUT/${TAG}_latency_shapes.txt
+echo "== ncu --set full of the warp-per-stream latency kernel (1024 streams)"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:chain_kernel_w -s 3 -c 1 -o $OUT/${TAG}_w16_full -f \
+    python tools/prof_one.py 1024 16 3 2 1 > $OUT/${TAG}_ncu_w_full.log 2>&1
+ncu -i $OUT/${TAG}_w16_full.ncu-rep --page details > $OUT/${TAG}_ncu_w16_details.txt 2>&1
