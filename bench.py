@@ -96,6 +96,15 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
+_JSON_FD = None
+
+
+def emit_json(out):
+    line = (json.dumps(out) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, line)
+
+
 def write_models(wl, tmpdir):
     from aidadsp_lv2_b200 import models
     paths = []
@@ -366,7 +375,7 @@ def run_ours(args, rank, world, local_rank):
             out["cpu_baseline"] = run_reference_sample(wl, 300, 3, paths, n_streams=min(n_local, 4096))
         except Exception as ex:  # the reference build is test infrastructure; its absence must not fail the GPU arm
             out["cpu_baseline"] = {"unavailable": str(ex)}
-    print(json.dumps(out), flush=True)
+    emit_json(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -432,7 +441,7 @@ def run_reference(args, rank, world):
                       "note": "CPU arm: host cores only, no GPU; each step renders a bounded sample (%d streams) of the workload; throughput is independent of the stream count on a CPU; runs once on rank 0 regardless of --gpus" % n},
            "realtime_streams": cb["realtime_streams"], "us_per_buffer": cb["us_per_buffer"], "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit_json(out)
 
 
 def main():
@@ -452,6 +461,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line: rank 0's JSON.  Native libraries write there too (NCCL prints its version banner
+    # on communicator creation, the reference prints layer info while parsing models), so file descriptor 1 is pointed
+    # at stderr for the whole run and the JSON line goes to the saved descriptor.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -175,3 +175,37 @@ def test_ten_seconds_per_kernel_shape(native_libs, bundled_models, tile_mode):
     # no drift growth: the last second stays within the reference's own build-to-build floor (2e-5)
     assert per_second[:, -1].max() <= max(4 * per_second[:, 1].max(), 2.5e-5), per_second
     eng.close()
+
+
+@pytest.mark.parametrize("tile_mode", [1, 2, 3])
+def test_block_size_invariance(native_libs, bundled_models, tile_mode):
+    """Size-independent property of the path: how the host cuts the signal into run() periods must not change a single
+    bit of the output -- every state (biquads, smoothers, h/c) is carried exactly.  Regular 128-sample periods vs a
+    ragged sequence that contains 1-sample periods, periods shorter than the systolic filter cascade's fill (12
+    iterations) and periods longer than a shared-memory sub-block; an LSTM-12 capture, a conditioned GRU-16 and an
+    LSTM-40, pre- and post-EQ, in the lowest-latency, the register-tiled and the tensor-core shape."""
+    ms = [models.load_json(bundled_models[0]), models.synthetic(1, 16, 3, seed=77), models.synthetic(0, 40, 1, seed=78)]
+    ctls = [ax.default_controls(EQPOS=1.0, BASS=3.0, MID=-2.0, TREBLE=4.0, PARAM1=0.3, PARAM2=0.8),
+            ax.default_controls(EQPOS=0.0, DEPTH=1.0, PRESENCE=2.0, MTYPE=1.0, PARAM1=0.9, PARAM2=0.1)]
+    cuts = {"regular": [128] * 8, "ragged": [1, 5, 37, 100, 3, 250, 128, 500]}
+    x = signals.sweep_noise_block(len(ms) * len(ctls), 1024)
+    outs = {}
+    for name, blocks in cuts.items():
+        assert sum(blocks) == 1024
+        eng = ax.Engine(max_streams=64, max_block=512)
+        eng.configure(tile_mode=tile_mode, math_mode=0)
+        for m in ms:
+            mid = eng.register_model(m)
+            for c in ctls:
+                s = eng.open_stream()
+                eng.set_model(s, mid)
+                eng.set_controls(s, c, loading=False)
+        y = np.empty_like(x)
+        pos = 0
+        for n in blocks:
+            y[:, pos:pos + n] = eng.render_host(np.ascontiguousarray(x[:, pos:pos + n]))
+            pos += n
+        outs[name] = y
+        eng.close()
+    assert np.isfinite(outs["regular"]).all() and np.abs(outs["regular"]).max() > 1e-3
+    assert np.array_equal(outs["regular"], outs["ragged"]), np.abs(outs["regular"] - outs["ragged"]).max(axis=1)
