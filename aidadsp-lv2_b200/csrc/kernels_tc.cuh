@@ -47,6 +47,9 @@
 #ifndef AIDAX_A_RN
 #define AIDAX_A_RN 0 // recurrent vector: same (one more integer add per element and step)
 #endif
+#ifndef AIDAX_EARLY_HALF
+#define AIDAX_EARLY_HALF 0
+#endif
 #ifndef AIDAX_DESC64
 #define AIDAX_DESC64 0 // 1: carry full 64-bit operand descriptors instead of their low words
 #endif
@@ -70,8 +73,13 @@ struct TcShape {
     static constexpr int KX = H;                 // first input row: x, p1, p2, then the constant 1 that carries the bias
     static constexpr int KP = (H + 4 + 7) / 8 * 8; // K padded to the tf32 MMA depth (8)
     static constexpr int KSTEPS = KP / 8;
-    static constexpr int NSPLIT = N > 256 ? 2 : 1; // one MMA covers at most N = 256
+    // The accumulator is produced in NSPLIT column halves with their own completion barrier (all MMAs of half 0 are
+    // issued and committed first): the epilogue of the first hidden units starts while the tensor core still works
+    // on the second half.  Needs halves that are legal MMA widths (multiple of 16) and more than one epilogue group.
+    static constexpr int NSPLIT = (AIDAX_EARLY_HALF && (N / 2) % 16 == 0 && H >= 16) ? 2 : 1;
     static constexpr int NMMA = N / NSPLIT;
+    // first epilogue group (pair of 16-column chunks) that needs columns of the second half
+    static constexpr int QWAIT = NSPLIT == 1 ? 0 : ((NMMA / 16) & ~1);
     static constexpr int A_FLOATS = 128 * KP;    // one of (hi, lo)
     static constexpr int B_FLOATS = N * KP;
     static constexpr int XP = 33;                // pitch of the per-warp audio tile (odd: conflict free both ways)
@@ -86,7 +94,7 @@ struct TcShape {
     // floats of shared memory that do not depend on the sub-block length
     __host__ __device__ static constexpr int fixed_floats(int nt)
     {
-        return 2 * B_FLOATS + nt * 2 * A_FLOATS + (H + 4) /* dense w, b */ + 2 * nt /* mbarriers */ + 4 /* tmem base + pad */;
+        return 2 * B_FLOATS + nt * 2 * A_FLOATS + (H + 4) /* dense w, b */ + 4 * nt /* mbarriers: 2 per tile */ + 4 /* tmem base + pad */;
     }
     __host__ __device__ static constexpr int warp_floats(int ts, int n_param_tiles) { return 32 + ts * XP * (1 + n_param_tiles); }
 };
@@ -150,19 +158,19 @@ struct TcCell {
 #endif
         const tc_desc_t a_hi = tt.da_hi, a_lo = tt.da_lo, b_hi = tt.db_hi, b_lo = tt.db_lo;
 #pragma unroll
-        for (int ks = 0; ks < S::KSTEPS; ++ks) {
-            const uint32_t ao = (ks * 2 * LBO_A) >> 4, bo = (ks * 2 * LBO_B) >> 4;
+        for (int nh = 0; nh < S::NSPLIT; ++nh) {
+            const uint32_t d = tt.tmem_d + nh * S::NMMA;
 #pragma unroll
-            for (int nh = 0; nh < S::NSPLIT; ++nh) {
-                const uint32_t d = tt.tmem_d + nh * S::NMMA;
+            for (int ks = 0; ks < S::KSTEPS; ++ks) {
+                const uint32_t ao = (ks * 2 * LBO_A) >> 4, bo = (ks * 2 * LBO_B) >> 4;
                 const uint32_t bn = bo + ((nh * S::NMMA * 16) >> 4);
                 // smallest terms first
                 tc::mma_tf32(d, HIW | (a_lo + ao), HIW | (b_hi + bn), idesc, ks > 0);
                 tc::mma_tf32(d, HIW | (a_hi + ao), HIW | (b_lo + bn), idesc, 1);
                 tc::mma_tf32(d, HIW | (a_hi + ao), HIW | (b_hi + bn), idesc, 1);
             }
+            tc::mma_commit(tt.bar_addr + 8 * nh); // fires when every MMA issued so far has completed
         }
-        tc::mma_commit(tt.bar_addr);
     }
 
     // accumulator column of (hidden unit u, gate lane g).  Within a 16-column chunk of 4 units the order is
@@ -455,10 +463,21 @@ struct TcCell {
             // epilogue: groups of two 16-column chunks (8 hidden units) are loaded together and evaluated as one
             // straight-line block, so the 8 + 2 batched reciprocal chains of a group overlap each other's MUFU latency
             float2 y2 = make_float2(db, 0.f);
+            // h(t) of the groups evaluated before the second accumulator half is complete: the MMAs still in flight read
+            // h(t-1) from the A tile, so these stores wait for them
+            float2 pend[S::QWAIT > 0 ? S::QWAIT * 2 : 1];
 #pragma unroll
             for (int q = 0; q < H / 4; q += AIDAX_TC_GROUP) {
                 constexpr int NQ = H / 4;
                 const bool two = AIDAX_TC_GROUP == 2 && q + 1 < NQ;
+                if (S::NSPLIT == 2 && q == S::QWAIT) {
+#if !(AIDAX_WHATIF & 1)
+                    tc::mbar_wait(tt.bar_addr + 8, tt.phase ^ 1u); // tt.phase was flipped after the first half's wait
+                    tc::tc_fence_after();
+#endif
+#pragma unroll
+                    for (int c = 0; c < S::QWAIT; ++c) store_chunk(tt, c, pend[2 * c], pend[2 * c + 1]);
+                }
                 uint32_t raw0[16], raw1[16];
                 tc::tmem_ld16(tt.tmem_ld + 16 * q, raw0);
                 if (two) tc::tmem_ld16(tt.tmem_ld + 16 * (q + 1), raw1);
@@ -471,13 +490,16 @@ struct TcCell {
                     eval_group<false>(raw0, raw0, q, cst, hn);
                 }
                 const float2* dw2 = reinterpret_cast<const float2*>(tt.dw + 4 * q);
+                const bool hold = S::NSPLIT == 2 && q < S::QWAIT;
                 y2 = tc::fma2(dw2[0], hn[0], y2);
                 y2 = tc::fma2(dw2[1], hn[1], y2);
-                store_chunk(tt, q, hn[0], hn[1]);
+                if (hold) { pend[2 * q] = hn[0]; pend[2 * q + 1] = hn[1]; }
+                else store_chunk(tt, q, hn[0], hn[1]);
                 if (two) {
                     y2 = tc::fma2(dw2[2], hn[2], y2);
                     y2 = tc::fma2(dw2[3], hn[3], y2);
-                    store_chunk(tt, q + 1, hn[2], hn[3]);
+                    if (hold) { pend[2 * q + 2] = hn[2]; pend[2 * q + 3] = hn[3]; }
+                    else store_chunk(tt, q + 1, hn[2], hn[3]);
                 }
             }
             // dense + skip + output gain (applyModel, rt-neural-generic.cpp:170-182)
@@ -514,7 +536,7 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
     float* Abase = Bl + S::B_FLOATS;
     float* dw = Abase + NT * 2 * S::A_FLOATS;
     uint64_t* bars = reinterpret_cast<uint64_t*>(dw + H + 4);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NT);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NT);
 
     const ModelDev md = p.models[p.blk_model[blk]];
     const int input_size = md.input_size;
@@ -548,7 +570,7 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
     }
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < NT; ++i) tc::mbar_init(&bars[i], 1);
+        for (int i = 0; i < 2 * NT; ++i) tc::mbar_init(&bars[i], 1);
         tc::mbar_init_fence();
     }
     if (warp == 0) tc::tmem_alloc(tmem_slot, S::tmem_cols(NT));
@@ -569,7 +591,7 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
         tt.db_hi = (tc_desc_t)tc::make_smem_desc(tc::smem_u32(Bh), LBO_B, SBO);
         tt.db_lo = (tc_desc_t)tc::make_smem_desc(tc::smem_u32(Bl), LBO_B, SBO);
     }
-    tt.bar_addr = tc::smem_u32(&bars[tile]);
+    tt.bar_addr = tc::smem_u32(&bars[2 * tile]); // + 8: the second accumulator half's barrier
     tt.phase = 0;
     tt.tmem_d = tmem_base + tile * S::N;
     tt.tmem_ld = tt.tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
