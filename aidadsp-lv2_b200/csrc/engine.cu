@@ -136,7 +136,10 @@ struct aidax_engine {
     cudaStream_t kstream[kMaxKernelStreams] = {};
     int n_kstreams = 4;
     cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_fan_fork = nullptr, ev_fan_join[kMaxKernelStreams] = {}; // family fan-out inside one range (launch_all)
+    int fan_next = 0;
     std::vector<cudaEvent_t> ev_in, ev_done, ev_out;
+    bool debug_sync = false; // AIDAX_DEBUG_SYNC=1: synchronise after every kernel launch and report which one faulted
     bool trace = false;      // AIDAX_TRACE=1: per-range timeline of the host-fed pipeline on stderr
     int trace_left = 3;
     struct PendingRange { int first, n, n_samples; };
@@ -226,6 +229,8 @@ static cudaError_t upload_rows(aidax_engine* e, cudaStream_t st, T* dev, const T
                              rows, cudaMemcpyHostToDevice, st);
 }
 
+static cudaError_t sync_kernel_streams(aidax_engine* e);
+
 static int upload_dirty(aidax_engine* e, int first, int n, cudaStream_t st)
 {
     if (e->models_dirty) {
@@ -255,6 +260,14 @@ static int upload_dirty(aidax_engine* e, int first, int n, cudaStream_t st)
             if ((s < first || s >= last) && (e->dirty_ctrl[s] || e->dirty_coef[s] || e->dirty_cmd[s])) remaining = true;
     }
     e->any_dirty = remaining;
+    // Control uploads of this range must not overlap the kernels of ranges submitted earlier in the same period.
+    // Measured on B200 (tools/c4_probe.py): with the hand-over of a model-binding period streaming (range A's 2048-step
+    // pre-warm kernel still running on its kernel stream while range B's pageable-memory uploads are issued on
+    // another), the FP32 latency shapes of H = 20 fault with "illegal memory access" although the column ranges are
+    // disjoint and compute-sanitizer sees no invalid access when the same work runs serialised; with this wait in
+    // place -- or with one kernel stream -- every mix of models passes.  Root cause not identified yet.
+    // Steady-state periods upload nothing and never get here, so the streaming overlap is unaffected.
+    if (!e->pending.empty() && (chi > clo || fhi > flo || mhi > mlo)) CUDA_TRY(sync_kernel_streams(e));
     CUDA_TRY(upload_rows(e, st, e->d_flags.d, e->h_flags.data(), 1, clo, chi));
     CUDA_TRY(upload_rows(e, st, e->d_pre_target.d, e->h_pre_target.data(), 1, clo, chi));
     CUDA_TRY(upload_rows(e, st, e->d_master_target.d, e->h_master_target.data(), 1, clo, chi));
@@ -372,8 +385,25 @@ static int launch_all(aidax_engine* e, cudaStream_t st, int first, int n, int n_
     RangePlan* rp = nullptr;
     rc = build_plan(e, first, n, &rp);
     if (rc) return rc;
+    // A range with several kernel families (heterogeneous models, C4) fans its launches out over the kernel streams:
+    // the families own disjoint streams, each launch alone underfills the GPU (a few thousand streams), and run one
+    // after the other they cost the sum of their latencies.  Fork from / join back into `st` with events, so callers
+    // keep seeing one ordered stream.
+    const bool fan = rp->launches.size() > 1 && e->n_kstreams > 1 && !e->debug_sync;
+    if (fan) CUDA_TRY(cudaEventRecord(e->ev_fan_fork, st));
+    unsigned used = 0;
+    int li = 0;
     for (const LaunchPlan& lp : rp->launches) {
         const KernelVariant* kv = lp.kv;
+        cudaStream_t ls = st;
+        if (fan) {
+            const int k = (e->fan_next + li++) % e->n_kstreams;
+            if (e->kstream[k] != st) {
+                ls = e->kstream[k];
+                if (!(used & (1u << k))) CUDA_TRY(cudaStreamWaitEvent(ls, e->ev_fan_fork, 0));
+                used |= 1u << k;
+            }
+        }
         // samples per shared-memory sub-block: as many as fit with the variant's target residency, capped at the period
         int ts = n_samples;
         const size_t budget = std::min(e->smem_optin, e->smem_per_sm / (size_t)kv->ctas_per_sm - 1024);
@@ -398,8 +428,22 @@ static int launch_all(aidax_engine* e, cudaStream_t st, int first, int n, int n_
         p.models = e->d_models.d;
         p.sa = e->sa();
         void* args[] = {&p};
-        CUDA_TRY(cudaLaunchKernel(fn, dim3(lp.n_blocks), dim3(kv->NW * 32), args, smem, st));
+        CUDA_TRY(cudaLaunchKernel(fn, dim3(lp.n_blocks), dim3(kv->NW * 32), args, smem, ls));
         e->launches++;
+        if (e->debug_sync) { // AIDAX_DEBUG_SYNC=1: attribute an asynchronous fault to the launch that caused it
+            const cudaError_t err = cudaStreamSynchronize(ls);
+            if (err != cudaSuccess)
+                return fail(AIDAX_ERR_CUDA, "kernel fault: %s -- cell %d H %d L %d S %d kind %d, range [%d +%d), %d blocks x %d threads, ts %d, smem %zu, layout %d",
+                            cudaGetErrorString(err), kv->cell, kv->H, kv->L, kv->S, kv->kind, first, n, lp.n_blocks, kv->NW * 32, ts, smem, layout);
+        }
+    }
+    if (fan) {
+        e->fan_next = (e->fan_next + li) % e->n_kstreams;
+        for (int k = 0; k < e->n_kstreams; ++k)
+            if (used & (1u << k)) {
+                CUDA_TRY(cudaEventRecord(e->ev_fan_join[k], e->kstream[k]));
+                CUDA_TRY(cudaStreamWaitEvent(st, e->ev_fan_join[k], 0));
+            }
     }
     return AIDAX_OK;
 }
@@ -456,6 +500,7 @@ int aidax_engine_create(int device, int max_streams, int max_block, aidax_engine
     e->smem_optin = prop.sharedMemPerBlockOptin;
     e->smem_per_sm = prop.sharedMemPerMultiprocessor;
     if (const char* v = std::getenv("AIDAX_TC_MIN_STREAMS")) e->tc_min_streams = std::atoi(v);
+    if (const char* v = std::getenv("AIDAX_TILE_MODE")) e->tile_mode = std::max(0, std::min(std::atoi(v), 3)); // initial kernel-shape choice (aidax_engine_configure overrides)
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_out, cudaStreamNonBlocking));
@@ -463,7 +508,10 @@ int aidax_engine_create(int device, int max_streams, int max_block, aidax_engine
     e->kstream[0] = e->stream;
     for (int k = 1; k < e->n_kstreams; ++k) CUDA_TRY(cudaStreamCreateWithFlags(&e->kstream[k], cudaStreamNonBlocking));
     e->trace = std::getenv("AIDAX_TRACE") != nullptr;
+    e->debug_sync = std::getenv("AIDAX_DEBUG_SYNC") != nullptr;
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, e->trace ? cudaEventDefault : cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fan_fork, cudaEventDisableTiming));
+    for (int k = 0; k < e->n_kstreams; ++k) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fan_join[k], cudaEventDisableTiming));
     const size_t cap = (size_t)e->cap;
     e->streams.resize(cap);
     e->dirty_ctrl.assign(cap, 0); e->dirty_coef.assign(cap, 0); e->dirty_cmd.assign(cap, 0);
@@ -506,6 +554,8 @@ int aidax_engine_destroy(aidax_engine* e)
     for (cudaEvent_t ev : e->ev_done) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->ev_out) cudaEventDestroy(ev);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_fan_fork) cudaEventDestroy(e->ev_fan_fork);
+    for (cudaEvent_t ev : e->ev_fan_join) if (ev) cudaEventDestroy(ev);
     for (int k = 1; k < e->n_kstreams; ++k) if (e->kstream[k]) cudaStreamDestroy(e->kstream[k]);
     if (e->stream_in) cudaStreamDestroy(e->stream_in);
     if (e->stream_out) cudaStreamDestroy(e->stream_out);

@@ -258,3 +258,46 @@ def test_streaming_chunk_handover_equals_single_render(native_libs, tmp_path):
     assert peak > 1e-3
     assert launches >= 4 * 11, "expected one launch per 256-stream chunk per period, saw %d launches" % launches
     assert err <= 2e-6, "chunked hand-over differs from a single render: %g" % err
+
+
+_MIXED_CHILD = r"""
+import os, sys, tempfile
+sys.path.insert(0, os.environ["AIDAX_REPO"])
+import numpy as np
+import aidadsp_lv2_b200 as ax
+from aidadsp_lv2_b200 import models
+n, per = int(sys.argv[1]), 1024
+ms = [models.synthetic(0, h, 1, seed=200 + h) for h in (8, 12, 16, 20, 24, 32, 40)]
+tmp = tempfile.mkdtemp(prefix="aidax_mixed_")
+paths = []
+for k, m in enumerate(ms):
+    p = os.path.join(tmp, "m%d.json" % k); models.save_json(m, p); paths.append(p)
+host = ax.BatchHost(ax.plugin_path(), n_instances=n, max_block=128, n_threads=8, device=0)
+for s in range(n):
+    host.load_model(paths[(s // per) % len(paths)], instance=s)
+rng = np.random.default_rng(3)
+host.input[:, :128] = (rng.random((n, 128), dtype=np.float32) - 0.5) * 0.2
+for i in range(5):
+    host.run(128)   # period 1 binds the models: control uploads + 2048-step pre-warm kernels, range after range
+y = host.output[:, :128].copy()
+print("RESULT", float(np.abs(y).max()), int(np.isfinite(y).all()), host.launch_count, float(np.abs(y[:per] - y[7 * per:8 * per]).max()))
+"""
+
+
+@pytest.mark.parametrize("tile_mode", ["0", "1"])
+def test_streaming_handover_with_mixed_models(native_libs, tmp_path, tile_mode):
+    """Regression (found with the C4 workload through the plugin path): 32768 instances over seven LSTM models of
+    different hidden sizes, handed over in 16384-stream ranges on several kernel streams.  The model-binding period --
+    control uploads of one range while the previous range's pre-warm kernels are still running -- used to end in an
+    illegal memory access with the FP32 latency shapes.  Every period must complete with finite, non-silent output."""
+    import subprocess
+    import sys
+    child = tmp_path / "mixed.py"
+    child.write_text(_MIXED_CHILD)
+    env = dict(os.environ, AIDAX_TILE_MODE=tile_mode, AIDAX_REPO=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, str(child), "32768"], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][-1].split()
+    peak, finite, launches = float(line[1]), int(line[2]), int(line[3])
+    assert finite == 1 and peak > 1e-3
+    assert launches >= 5
