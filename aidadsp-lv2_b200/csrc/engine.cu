@@ -139,10 +139,17 @@ struct aidax_engine {
     cudaEvent_t ev_fan_fork = nullptr, ev_fan_join[kMaxKernelStreams] = {}; // family fan-out inside one range (launch_all)
     int fan_next = 0;
     std::vector<cudaEvent_t> ev_in, ev_done, ev_out;
+    bool defer_hetero = false; // AIDAX_DEFER_HETERO=1: render the heterogeneous hand-over ranges of a period together (submit_range)
     bool debug_sync = false; // AIDAX_DEBUG_SYNC=1: synchronise after every kernel launch and report which one faulted
     bool trace = false;      // AIDAX_TRACE=1: per-range timeline of the host-fed pipeline on stderr
     int trace_left = 3;
-    struct PendingRange { int first, n, n_samples; };
+    struct PendingRange {
+        int first, n, n_samples;
+        bool deferred;      // kernels not launched yet: the range waits for the period's other heterogeneous ranges (wait_ranges)
+        float* out;         // deferred copy-out target
+        size_t stride;
+        int layout;
+    };
     std::vector<PendingRange> pending;
 
     StreamArrays sa() const
@@ -509,6 +516,7 @@ int aidax_engine_create(int device, int max_streams, int max_block, aidax_engine
     for (int k = 1; k < e->n_kstreams; ++k) CUDA_TRY(cudaStreamCreateWithFlags(&e->kstream[k], cudaStreamNonBlocking));
     e->trace = std::getenv("AIDAX_TRACE") != nullptr;
     e->debug_sync = std::getenv("AIDAX_DEBUG_SYNC") != nullptr;
+    if (const char* v = std::getenv("AIDAX_DEFER_HETERO")) e->defer_hetero = std::atoi(v) != 0;
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, e->trace ? cudaEventDefault : cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fan_fork, cudaEventDisableTiming));
     for (int k = 0; k < e->n_kstreams; ++k) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fan_join[k], cudaEventDisableTiming));
@@ -918,6 +926,25 @@ static int submit_range(aidax_engine* e, int first_stream, int n_streams, int n_
         CUDA_TRY(cudaMemcpy2DAsync(e->d_io_in.d + doff, cols * sizeof(float), in, stride * sizeof(float), cols * sizeof(float), rows,
                                    cudaMemcpyHostToDevice, s_in));
     }
+    // A range that holds several kernel families (heterogeneous models) and is one of many hand-over ranges of a period
+    // is NOT rendered on its own: cutting the period into ranges cuts every family into pieces too small for the
+    // throughput shapes (C4 through the plugins: 14 families of 1-2 k streams per range ran the FP32 latency shapes,
+    // 5.5 ms per period against 1.8 ms device-resident).  Its input and controls go to the device now, its kernels are
+    // launched per family over all such ranges at once when the period is complete (wait_ranges).
+    bool defer = false;
+    if (!serial && e->defer_hetero && layout == AIDAX_LAYOUT_PLANAR && n_samples == e->max_block && stride == cols) {
+        RangePlan* rp = nullptr;
+        int rcp = build_plan(e, first_stream, n_streams, &rp);
+        if (rcp) return rcp;
+        defer = rp->launches.size() > 1;
+    }
+    if (defer) {
+        int rcu = upload_dirty(e, first_stream, n_streams, s_in);
+        if (rcu) return rcu;
+        CUDA_TRY(cudaEventRecord(e->ev_in[idx], s_in));
+        e->pending.push_back(aidax_engine::PendingRange{first_stream, n_streams, n_samples, true, out, stride, layout});
+        return AIDAX_OK;
+    }
     if (!serial) {
         CUDA_TRY(cudaEventRecord(e->ev_in[idx], s_in));
         CUDA_TRY(cudaStreamWaitEvent(ks, e->ev_in[idx], 0));
@@ -935,13 +962,49 @@ static int submit_range(aidax_engine* e, int first_stream, int n_streams, int n_
                                    cudaMemcpyDeviceToHost, s_out));
     }
     if (e->trace && !serial) CUDA_TRY(cudaEventRecord(e->ev_out[idx], s_out));
-    e->pending.push_back(aidax_engine::PendingRange{first_stream, n_streams, n_samples});
+    e->pending.push_back(aidax_engine::PendingRange{first_stream, n_streams, n_samples, false, nullptr, 0, layout});
+    return AIDAX_OK;
+}
+
+// Kernels and copy-out of the ranges submit_range deferred: runs of adjacent ranges are rendered as one range each.
+static int flush_deferred(aidax_engine* e)
+{
+    std::vector<size_t> order;
+    for (size_t i = 0; i < e->pending.size(); ++i) if (e->pending[i].deferred) order.push_back(i);
+    if (order.empty()) return AIDAX_OK;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return e->pending[a].first < e->pending[b].first; });
+    for (size_t a = 0; a < order.size();) {
+        size_t b = a + 1;
+        const aidax_engine::PendingRange& r0 = e->pending[order[a]];
+        int end = r0.first + r0.n;
+        while (b < order.size() && e->pending[order[b]].first == end && e->pending[order[b]].n_samples == r0.n_samples) {
+            end += e->pending[order[b]].n;
+            ++b;
+        }
+        for (size_t k = a; k < b; ++k) CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_in[order[k]], 0));
+        const size_t doff = (size_t)r0.first * (size_t)e->max_block;
+        const int rc = launch_all(e, e->stream, r0.first, end - r0.first, r0.n_samples, e->d_io_in.d + doff, e->d_io_out.d + doff, r0.layout,
+                                  (size_t)r0.n_samples);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(e->ev_done[order[a]], e->stream));
+        CUDA_TRY(cudaStreamWaitEvent(e->stream_out, e->ev_done[order[a]], 0));
+        for (size_t k = a; k < b; ++k) {
+            const aidax_engine::PendingRange& r = e->pending[order[k]];
+            const size_t off = (size_t)r.first * (size_t)e->max_block;
+            CUDA_TRY(cudaMemcpyAsync(r.out, e->d_io_out.d + off, (size_t)r.n * (size_t)r.n_samples * sizeof(float), cudaMemcpyDeviceToHost,
+                                     e->stream_out));
+            if (k != a) CUDA_TRY(cudaEventRecord(e->ev_done[order[k]], e->stream));
+            if (e->trace) CUDA_TRY(cudaEventRecord(e->ev_out[order[k]], e->stream_out));
+        }
+        a = b;
+    }
     return AIDAX_OK;
 }
 
 static int wait_ranges(aidax_engine* e)
 {
     if (e->pending.empty()) return AIDAX_OK;
+    const int rc_flush = flush_deferred(e);
     // every D2H copy is on stream_out and waits for its kernel, so this covers the kernel streams too;
     // the engine stream is re-joined so that later aidax_render_device calls stay ordered after this period
     cudaError_t err = sync_kernel_streams(e);
@@ -960,7 +1023,7 @@ static int wait_ranges(aidax_engine* e)
     for (const aidax_engine::PendingRange& r : e->pending) after_render(e, r.first, r.n, r.n_samples);
     e->pending.clear();
     CUDA_TRY(err);
-    return AIDAX_OK;
+    return rc_flush;
 }
 
 static int render_host_checks(aidax_engine* e, int first_stream, int n_streams, int n_samples, const float* in, float* out, int layout, size_t stride)
