@@ -139,7 +139,7 @@ struct aidax_engine {
     cudaEvent_t ev_fan_fork = nullptr, ev_fan_join[kMaxKernelStreams] = {}; // family fan-out inside one range (launch_all)
     int fan_next = 0;
     std::vector<cudaEvent_t> ev_in, ev_done, ev_out;
-    bool defer_hetero = false; // AIDAX_DEFER_HETERO=1: render the heterogeneous hand-over ranges of a period together (submit_range)
+    bool defer_hetero = true; // AIDAX_DEFER_HETERO=0: render heterogeneous hand-over ranges one by one (submit_range)
     bool debug_sync = false; // AIDAX_DEBUG_SYNC=1: synchronise after every kernel launch and report which one faulted
     bool trace = false;      // AIDAX_TRACE=1: per-range timeline of the host-fed pipeline on stderr
     int trace_left = 3;
