@@ -284,17 +284,20 @@ print("RESULT", float(np.abs(y).max()), int(np.isfinite(y).all()), host.launch_c
 """
 
 
-@pytest.mark.parametrize("tile_mode", ["0", "1"])
-def test_streaming_handover_with_mixed_models(native_libs, tmp_path, tile_mode):
+@pytest.mark.parametrize("tile_mode,defer", [("0", "1"), ("1", "1"), ("1", "0")])
+def test_streaming_handover_with_mixed_models(native_libs, tmp_path, tile_mode, defer):
     """Regression (found with the C4 workload through the plugin path): 32768 instances over seven LSTM models of
     different hidden sizes, handed over in 16384-stream ranges on several kernel streams.  The model-binding period --
     control uploads of one range while the previous range's pre-warm kernels are still running -- used to end in an
-    illegal memory access with the FP32 latency shapes.  Every period must complete with finite, non-silent output."""
+    illegal memory access with the FP32 latency shapes.  Every period must complete with finite, non-silent output.
+    defer = "1": the engine's default, mixed-family ranges are rendered together at the end of the period;
+    defer = "0": range by range, the path the fault was found on (upload_dirty now orders uploads after in-flight kernels)."""
     import subprocess
     import sys
     child = tmp_path / "mixed.py"
     child.write_text(_MIXED_CHILD)
-    env = dict(os.environ, AIDAX_TILE_MODE=tile_mode, AIDAX_REPO=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, AIDAX_TILE_MODE=tile_mode, AIDAX_DEFER_HETERO=defer,
+               AIDAX_REPO=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     out = subprocess.run([sys.executable, str(child), "32768"], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][-1].split()
