@@ -109,6 +109,7 @@ struct aidax_engine {
     std::vector<uint32_t> h_flags, h_cmd;
     std::vector<float> h_pre_target, h_master_target, h_p_port, h_p_init, h_cmd_pre_mem, h_cmd_master_mem, h_exp_coef, h_lin_denom;
     std::vector<double> h_bq_coef;
+    bool upload_order = true;    // AIDAX_UPLOAD_ORDER=0 (diagnosis only): let control uploads overlap in-flight kernels, see upload_dirty
     bool any_dirty = false;
 
     // device arrays
@@ -272,9 +273,10 @@ static int upload_dirty(aidax_engine* e, int first, int n, cudaStream_t st)
     // pre-warm kernel still running on its kernel stream while range B's pageable-memory uploads are issued on
     // another), the FP32 latency shapes of H = 20 fault with "illegal memory access" although the column ranges are
     // disjoint and compute-sanitizer sees no invalid access when the same work runs serialised; with this wait in
-    // place -- or with one kernel stream -- every mix of models passes.  Root cause not identified yet.
+    // place -- or with one kernel stream -- every mix of models passes.  Page-locking the shadows does not change it, so
+    // it is not the staged pageable copy path.  Root cause not identified yet.
     // Steady-state periods upload nothing and never get here, so the streaming overlap is unaffected.
-    if (!e->pending.empty() && (chi > clo || fhi > flo || mhi > mlo)) CUDA_TRY(sync_kernel_streams(e));
+    if (e->upload_order && !e->pending.empty() && (chi > clo || fhi > flo || mhi > mlo)) CUDA_TRY(sync_kernel_streams(e));
     CUDA_TRY(upload_rows(e, st, e->d_flags.d, e->h_flags.data(), 1, clo, chi));
     CUDA_TRY(upload_rows(e, st, e->d_pre_target.d, e->h_pre_target.data(), 1, clo, chi));
     CUDA_TRY(upload_rows(e, st, e->d_master_target.d, e->h_master_target.data(), 1, clo, chi));
@@ -530,6 +532,7 @@ int aidax_engine_create(int device, int max_streams, int max_block, aidax_engine
     e->h_cmd_pre_mem.assign(cap, 0.f); e->h_cmd_master_mem.assign(cap, 0.f);
     e->h_exp_coef.assign(cap, 0.f); e->h_lin_denom.assign(cap, 4800.f);
     e->h_bq_coef.assign((size_t)kNumBiquads * 5 * cap, 0.0);
+    if (const char* v = std::getenv("AIDAX_UPLOAD_ORDER")) e->upload_order = std::atoi(v) != 0;
     CUDA_TRY(e->d_flags.alloc(cap)); CUDA_TRY(e->d_cmd.alloc(cap)); CUDA_TRY(e->d_dflags.alloc(cap));
     CUDA_TRY(e->d_pre_target.alloc(cap)); CUDA_TRY(e->d_master_target.alloc(cap));
     CUDA_TRY(e->d_p_port.alloc(2 * cap)); CUDA_TRY(e->d_p_init.alloc(2 * cap));
