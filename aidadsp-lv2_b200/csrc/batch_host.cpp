@@ -1,6 +1,8 @@
 // batch_host.cpp -- libaidax_host.so: a minimal, multi-instance LV2 host for rt-neural-generic
 // binaries (see include/aidax_host.h).  No CUDA here: the GPU is reached only through the plugin.
 #include <dlfcn.h>
+#include <sched.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -78,11 +80,25 @@ char* map_abstract(LV2_State_Map_Path_Handle, const char* p) { return strdup(p);
 char* map_absolute(LV2_State_Map_Path_Handle, const char* p) { return strdup(p); }
 
 // ------------------------------------------------------------------ a tiny thread pool
+// pins the calling thread to one cpu (best effort)
+void pin_self(int cpu)
+{
+    if (cpu < 0) return;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    CPU_SET(cpu, &set);
+    sched_setaffinity(0, sizeof(set), &set);
+}
+
 class Pool {
 public:
-    explicit Pool(int n) : n_(std::max(1, n))
+    // cpus: one entry per worker (worker 0 is the thread that calls run()), empty = leave the scheduler alone
+    Pool(int n, const std::vector<int>& cpus) : n_(std::max(1, n)), cpus_(cpus)
     {
-        for (int i = 1; i < n_; ++i) threads_.emplace_back([this, i] { loop(i); });
+        for (int i = 1; i < n_; ++i) threads_.emplace_back([this, i] {
+            if (!cpus_.empty()) pin_self(cpus_[(size_t)i % cpus_.size()]);
+            loop(i);
+        });
     }
     ~Pool()
     {
@@ -132,6 +148,7 @@ private:
         }
     }
     int n_;
+    std::vector<int> cpus_;
     std::vector<std::thread> threads_;
     std::mutex mu_;
     std::condition_variable cv_, done_cv_;
@@ -179,6 +196,14 @@ struct aidax_host {
     // what the per-period loop needs of an instance, packed (the full records below are touched on events only)
     struct Hot { LV2_Handle handle; uint8_t* notify_buf; bool control_pending; };
     std::vector<Hot> hot;
+    // bulk path (AidaxBatchInterface::run_block): the handles as one array and, per instance, whether this period it
+    // must go through run() itself -- a patch:Set is pending on its CONTROL port, or its NOTIFY port holds something
+    // other than the empty sequence its last run() left (first period; a notification the host has just consumed)
+    bool bulk = false;
+    std::vector<void*> handles;
+    std::vector<uint8_t> slow;
+    int n_active = 0;            // instances [0, n_active) take part in a period (aidax_host_set_active)
+    std::vector<int> cpus;       // cpus the pool is pinned to (empty = not pinned)
     std::vector<Instance> inst;
     std::vector<uint8_t> notify_storage;
     uint32_t notify_cap = 0;
@@ -243,6 +268,7 @@ void build_load_message(aidax_host* h, Instance& in, const char* path)
     in.control_pending = true;
     const size_t idx = (size_t)(&in - h->inst.data());
     if (idx < h->hot.size()) h->hot[idx].control_pending = true;
+    if (idx < h->slow.size()) h->slow[idx] = 1;
 }
 
 // count patch:Set notifications in an instance's NOTIFY buffer
@@ -262,10 +288,46 @@ void scan_notify(aidax_host* h, Instance& in)
     }
 }
 
+// run() of one instance the way an LV2 host calls it
+inline void run_one(aidax_host* h, int i, uint32_t n_samples, uint32_t notify_room)
+{
+    aidax_host::Hot& hot = h->hot[i];
+    // an LV2 host presents an output atom port as an empty chunk whose size is the capacity
+    LV2_Atom_Sequence* ns = (LV2_Atom_Sequence*)hot.notify_buf;
+    ns->atom.size = notify_room;
+    ns->atom.type = 0;
+    if (hot.control_pending) h->desc->connect_port(hot.handle, kPortControl, h->inst[i].control_buf.data());
+    h->desc->run(hot.handle, n_samples);
+    if (hot.control_pending) {
+        h->desc->connect_port(hot.handle, kPortControl, h->empty_seq);
+        hot.control_pending = false;
+        h->inst[i].control_pending = false;
+        h->inst[i].control_buf.clear();
+    }
+}
+
 void run_instances(aidax_host* h, int lo, int hi, uint32_t n_samples)
 {
-    constexpr int kAhead = 4;
     const uint32_t notify_room = h->notify_cap - (uint32_t)sizeof(LV2_Atom);
+    if (h->bulk) {
+        // instances with nothing pending go to the plugin in runs (a few ns each); the others one by one
+        uint8_t* slow = h->slow.data();
+        int i = lo;
+        while (i < hi) {
+            if (slow[i]) {
+                run_one(h, i, n_samples, notify_room);
+                slow[i] = 0;
+                ++i;
+                continue;
+            }
+            int j = i + 1;
+            while (j < hi && !slow[j]) ++j;
+            h->batch->run_block(h->handles.data() + i, (uint32_t)(j - i), n_samples);
+            i = j;
+        }
+        return;
+    }
+    constexpr int kAhead = 4;
     for (int i = lo; i < hi; ++i) {
         // run() of a small-state plugin is bound by cache misses on per-instance data that lives in several places
         // (plugin object, control row, notify buffer): start fetching a few instances ahead
@@ -279,19 +341,7 @@ void run_instances(aidax_host* h, int lo, int hi, uint32_t n_samples)
             __builtin_prefetch(h->ctl(i + kAhead, kFirstControl), 1);
             __builtin_prefetch(h->ctl(i + kAhead, kFirstControl + 16));
         }
-        aidax_host::Hot& hot = h->hot[i];
-        // an LV2 host presents an output atom port as an empty chunk whose size is the capacity
-        LV2_Atom_Sequence* ns = (LV2_Atom_Sequence*)hot.notify_buf;
-        ns->atom.size = notify_room;
-        ns->atom.type = 0;
-        if (hot.control_pending) h->desc->connect_port(hot.handle, kPortControl, h->inst[i].control_buf.data());
-        h->desc->run(hot.handle, n_samples);
-        if (hot.control_pending) {
-            h->desc->connect_port(hot.handle, kPortControl, h->empty_seq);
-            hot.control_pending = false;
-            h->inst[i].control_pending = false;
-            h->inst[i].control_buf.clear();
-        }
+        run_one(h, i, n_samples, notify_room);
     }
 }
 
@@ -311,6 +361,65 @@ void drain_worker(aidax_host* h, Instance& in)
             if (h->worker && h->worker->work_response) h->worker->work_response(in.handle, (uint32_t)w.data.size(), w.data.data());
         }
     }
+}
+
+// "0-3,8,10-11" -> {0,1,2,3,8,10,11}
+std::vector<int> parse_cpulist(const std::string& text)
+{
+    std::vector<int> out;
+    size_t i = 0;
+    while (i < text.size()) {
+        while (i < text.size() && !isdigit((unsigned char)text[i])) ++i;
+        if (i >= text.size()) break;
+        int a = 0;
+        while (i < text.size() && isdigit((unsigned char)text[i])) a = a * 10 + (text[i++] - '0');
+        int b = a;
+        if (i < text.size() && text[i] == '-') {
+            ++i;
+            b = 0;
+            while (i < text.size() && isdigit((unsigned char)text[i])) b = b * 10 + (text[i++] - '0');
+        }
+        for (int c = a; c <= b && out.size() < 4096; ++c) out.push_back(c);
+    }
+    return out;
+}
+
+// The cpus this process should run its period threads on: those local to the plugin's GPU (sysfs local_cpulist of
+// its PCI device) that the process is allowed to use, rotated by the rank of the process among the local ranks
+// (torchrun's LOCAL_RANK) so that processes driving neighbouring GPUs do not sit on each other's cores.
+cpu_set_t g_initial_affinity;   // of the thread that opened the first host, before any pinning
+bool g_have_initial_affinity = false;
+
+std::vector<int> gpu_local_cpus(const AidaxBatchInterface* batch, int n_threads)
+{
+    std::vector<int> allowed;
+    if (!g_have_initial_affinity) {
+        CPU_ZERO(&g_initial_affinity);
+        if (sched_getaffinity(0, sizeof(g_initial_affinity), &g_initial_affinity) != 0) return {};
+        g_have_initial_affinity = true;
+    }
+    const cpu_set_t& set = g_initial_affinity;
+    for (int c = 0; c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &set)) allowed.push_back(c);
+    std::vector<int> local;
+    char bus[64] = {0};
+    if (batch && batch->abi_version >= 2 && batch->device_pci_bus_id && batch->device_pci_bus_id(bus, (int)sizeof(bus)) == 0) {
+        const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+        if (FILE* f = fopen(path.c_str(), "r")) {
+            char line[4096] = {0};
+            if (fgets(line, sizeof(line), f)) {
+                for (int c : parse_cpulist(line))
+                    if (std::find(allowed.begin(), allowed.end(), c) != allowed.end()) local.push_back(c);
+            }
+            fclose(f);
+        }
+    }
+    if (local.empty()) local = allowed; // no NUMA information (or a VM without it): all allowed cpus
+    if (local.empty()) return {};
+    const char* lr = getenv("LOCAL_RANK");
+    const int rank = lr && *lr ? atoi(lr) : 0;
+    std::vector<int> out;
+    for (int t = 0; t < std::max(1, n_threads); ++t) out.push_back(local[(size_t)(rank * std::max(1, n_threads) + t) % local.size()]);
+    return out;
 }
 
 struct StateStore { std::string value; LV2_URID key = 0; };
@@ -380,6 +489,37 @@ aidax_host* aidax_host_open(const char* plugin_so, double sample_rate, int n_ins
         return nullptr;
     }
     if (no_batch) h->batch = nullptr;
+    h->bulk = h->batch && h->batch->abi_version >= 2 && h->batch->run_block && getenv("AIDAX_HOST_NO_BULK") == nullptr;
+
+    h->notify_cap = n_instances <= 8192 ? 2048u : 384u;
+    h->inst.resize(n_instances);
+    auto instantiate_one = [&](int i) -> bool {
+        Instance& in = h->inst[i];
+        in.host = h.get();
+        in.schedule.handle = &in;
+        in.schedule.schedule_work = schedule_cb;
+        in.f_map = LV2_Feature{LV2_URID__map, &h->map};
+        in.f_sched = LV2_Feature{LV2_WORKER__schedule, &in.schedule};
+        in.f_log = LV2_Feature{LV2_LOG__log, &h->log};
+        in.features[0] = &in.f_map; in.features[1] = &in.f_sched; in.features[2] = &in.f_log; in.features[3] = nullptr;
+        in.handle = h->desc->instantiate(h->desc, sample_rate, "", in.features);
+        if (!in.handle) {
+            set_err("instantiate failed for instance %d", i);
+            for (int k = 0; k < i; ++k) h->desc->cleanup(h->inst[k].handle);
+            return false;
+        }
+        return true;
+    };
+    // The first instance brings the plugin's engine (and with it the GPU) into existence; the period threads and the
+    // audio arenas are then placed next to that GPU: one thread per cpu, cpus local to the GPU's PCIe root, pinned
+    // memory first touched from there.  AIDAX_HOST_PIN=0 leaves everything to the scheduler.
+    if (!instantiate_one(0)) return nullptr;
+    const char* pin_env = getenv("AIDAX_HOST_PIN");
+    if (!(pin_env && *pin_env && atoi(pin_env) == 0)) {
+        h->cpus = gpu_local_cpus(h->batch, n_threads);
+        if (!h->cpus.empty()) pin_self(h->cpus[0]);
+    }
+
     if (h->batch) {
         h->in = (float*)h->batch->arena_alloc(arena_bytes);
         h->out = (float*)h->batch->arena_alloc(arena_bytes);
@@ -400,25 +540,11 @@ aidax_host* aidax_host_open(const char* plugin_so, double sample_rate, int n_ins
         *h->ctl(i, 4) = 66.216f; *h->ctl(i, 12) = 305.f; *h->ctl(i, 14) = 750.f; *h->ctl(i, 15) = 0.707f;
         *h->ctl(i, 18) = 2000.f; *h->ctl(i, 21) = 1.f; *h->ctl(i, 24) = 1.f;
     }
-    h->notify_cap = n_instances <= 8192 ? 2048u : 384u;
     h->notify_storage.assign((size_t)n_instances * h->notify_cap, 0);
-    h->inst.resize(n_instances);
     for (int i = 0; i < n_instances; ++i) {
+        if (i > 0 && !instantiate_one(i)) return nullptr;
         Instance& in = h->inst[i];
-        in.host = h.get();
-        in.schedule.handle = &in;
-        in.schedule.schedule_work = schedule_cb;
-        in.f_map = LV2_Feature{LV2_URID__map, &h->map};
-        in.f_sched = LV2_Feature{LV2_WORKER__schedule, &in.schedule};
-        in.f_log = LV2_Feature{LV2_LOG__log, &h->log};
-        in.features[0] = &in.f_map; in.features[1] = &in.f_sched; in.features[2] = &in.f_log; in.features[3] = nullptr;
         in.notify_buf = h->notify_storage.data() + (size_t)i * h->notify_cap;
-        in.handle = h->desc->instantiate(h->desc, sample_rate, "", in.features);
-        if (!in.handle) {
-            set_err("instantiate failed for instance %d", i);
-            for (int k = 0; k < i; ++k) h->desc->cleanup(h->inst[k].handle);
-            return nullptr;
-        }
         h->desc->connect_port(in.handle, kPortIn, h->in + (size_t)i * h->stride);
         h->desc->connect_port(in.handle, kPortOut, h->out + (size_t)i * h->stride);
         h->desc->connect_port(in.handle, kPortControl, h->empty_seq);
@@ -426,8 +552,14 @@ aidax_host* aidax_host_open(const char* plugin_so, double sample_rate, int n_ins
         for (int p = kFirstControl; p < kPortCount; ++p) h->desc->connect_port(in.handle, p, h->ctl(i, p));
     }
     h->hot.resize(n_instances);
-    for (int i = 0; i < n_instances; ++i) h->hot[i] = aidax_host::Hot{h->inst[i].handle, h->inst[i].notify_buf, false};
-    h->pool.reset(new Pool(n_threads));
+    h->handles.resize(n_instances);
+    h->slow.assign(n_instances, 1); // first period: every instance reads its ports through run()
+    for (int i = 0; i < n_instances; ++i) {
+        h->hot[i] = aidax_host::Hot{h->inst[i].handle, h->inst[i].notify_buf, false};
+        h->handles[i] = h->inst[i].handle;
+    }
+    h->n_active = n_instances;
+    h->pool.reset(new Pool(n_threads, h->cpus));
     return h.release();
 }
 
@@ -444,6 +576,7 @@ void aidax_host_close(aidax_host* h)
     else { free(h->in); free(h->out); }
     free(h->controls);
     // the plugin binary stays loaded: it may own process-wide state (CUDA context, engine)
+    if (!h->cpus.empty() && g_have_initial_affinity) sched_setaffinity(0, sizeof(g_initial_affinity), &g_initial_affinity);
     delete h;
 }
 
@@ -498,15 +631,16 @@ int aidax_host_run(aidax_host* h, int n_samples)
 {
     if (!h || n_samples < 0 || n_samples > h->max_block) { set_err("bad n_samples"); return 1; }
     const int nt = h->pool->size();
-    const int n = h->n;
+    const int n = h->n_active;
     int rc = 0;
     const auto t0 = std::chrono::steady_clock::now();
     if (h->batch) h->batch->begin();
     // Instances are handed out in ascending blocks, so all threads work on the same neighbourhood of the arena and the
     // plugin's batch extension sees its chunks complete one after another (it ships a chunk to the GPU as soon as the
     // last instance of the chunk has run); it also balances threads when run() itself computes (the reference).
+    // Blocks are multiples of 64 instances: the plugin counts arrivals per 64-stream block, one cache line per block.
     std::atomic<int> next{0};
-    const int grain = n >= 64 * nt ? 64 : std::max(1, n / (4 * nt));
+    const int grain = h->bulk ? (n >= 1024 * nt ? 1024 : 256) : (n >= 64 * nt ? 64 : std::max(1, n / (4 * nt)));
     h->pool->run([&](int) {
         for (;;) {
             const int lo = next.fetch_add(grain, std::memory_order_relaxed);
@@ -525,17 +659,36 @@ int aidax_host_run(aidax_host* h, int n_samples)
     h->n_periods += 1.0;
     if (h->any_scheduled.load(std::memory_order_relaxed)) {
         h->any_scheduled.store(false, std::memory_order_relaxed);
+        const int n_all = h->n;
         h->pool->run([&](int w) {
-            const int lo = (int)((int64_t)n * w / nt), hi = (int)((int64_t)n * (w + 1) / nt);
+            const int lo = (int)((int64_t)n_all * w / nt), hi = (int)((int64_t)n_all * (w + 1) / nt);
             for (int i = lo; i < hi; ++i) {
                 Instance& in = h->inst[i];
                 if (in.scheduled.empty() && in.responses.empty()) continue;
                 drain_worker(h, in);
                 scan_notify(h, in);
+                h->slow[i] = 1; // its NOTIFY port may hold a notification now: the next period resets it through run()
             }
         });
     }
     return rc;
+}
+
+int aidax_host_set_active(aidax_host* h, int n_active)
+{
+    if (!h || n_active < 0 || n_active > h->n) { set_err("bad active count"); return 1; }
+    h->n_active = n_active;
+    return 0;
+}
+
+int aidax_host_is_bulk(const aidax_host* h) { return h && h->bulk ? 1 : 0; }
+
+int aidax_host_cpus(const aidax_host* h, int* out, int cap)
+{
+    if (!h) return 0;
+    const int n = (int)h->cpus.size();
+    for (int i = 0; i < n && i < cap && out; ++i) out[i] = h->cpus[i];
+    return n;
 }
 
 int aidax_host_notify_count(const aidax_host* h, int instance)

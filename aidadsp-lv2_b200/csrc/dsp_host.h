@@ -132,7 +132,8 @@ struct StreamHost {
     // decoded values (mirrors of what is uploaded)
     uint32_t flags = 0;
     float pre_target = 1.f;    // preGain.setTargetValue(1.f) at instantiate
-    float master_target = 0.f; // masterGain.setTargetValue(0.f) at instantiate
+    float master_target = 0.f; // masterGain.setTargetValue(0.f) at instantiate; decoded eagerly (what the next enabled run() will set)
+    float master_seen = 0.f;   // the target the reference's masterGain really holds: only an ENABLED run() with n_samples > 0 sets it (:654)
     float param_target[2] = {0.f, 0.f}; // LinearValueSmoother targets as the reference would hold them
     BiquadCoef bq[kNumBiquads];
 };
@@ -173,7 +174,7 @@ inline void init_stream_host(StreamHost& s, double samplerate)
 inline uint32_t decode_controls(StreamHost& s, const float c[AIDAX_N_CONTROLS], bool loading, bool model_bound)
 {
     uint32_t redesigned = 0;
-    std::memcpy(s.ctrl, c, sizeof(float) * AIDAX_N_CONTROLS);
+    if (c != s.ctrl) std::memcpy(s.ctrl, c, sizeof(float) * AIDAX_N_CONTROLS); // (callers re-decode a stream's own latched row)
     s.have_ctrl = true;
     s.loading = loading;
 
@@ -233,9 +234,9 @@ inline uint32_t decode_controls(StreamHost& s, const float c[AIDAX_N_CONTROLS], 
     if (c[AIDAX_CTRL_DCBLOCKER] == 1.0f) f |= F_DC;
     if (model_bound && !net_bypass) f |= F_NET;
     s.flags = f;
-    // masterGain.setTargetValue only happens on the enabled path (:654); when disabled the
-    // smoother keeps its previous target, which is unobservable until the next enabled run
-    // overwrites it.
+    // masterGain.setTargetValue only happens on the enabled path with n_samples > 0 (:606-619, 654).  The kernels read
+    // master_target only for such runs, so it is decoded eagerly; activate() -- which snaps the smoother to the target
+    // the reference holds (:341-342) -- uses master_seen, maintained by track_run_targets after each render.
     s.master_target = loading ? 0.f : master;
     return redesigned;
 }
@@ -243,9 +244,11 @@ inline uint32_t decode_controls(StreamHost& s, const float c[AIDAX_N_CONTROLS], 
 // What the reference's LinearValueSmoother targets would be after a processed buffer
 // (rt-neural-generic.cpp:634-635 + ValueSmoother.hpp:209-216); used for old_param hand-over
 // to the next model (work(), :822-825).
-inline void track_param_targets(StreamHost& s, int n_samples)
+inline void track_run_targets(StreamHost& s, int n_samples)
 {
-    if (n_samples <= 0 || !(s.flags & F_ENABLED) || !(s.flags & F_NET)) return;
+    if (n_samples <= 0 || !(s.flags & F_ENABLED)) return;
+    s.master_seen = s.master_target;
+    if (!(s.flags & F_NET)) return;
     for (int i = 0; i < 2; ++i) {
         const float v = s.ctrl[AIDAX_CTRL_PARAM1 + i];
         if (float_not_equal(s.param_target[i], v)) s.param_target[i] = v;

@@ -1,8 +1,10 @@
 // engine.cu -- host side of the C ABI in include/aidax.h: stream/model bookkeeping, control
 // decode, dirty-range uploads, block tables and kernel launches.  CUDA runtime only (no torch).
 #include <cuda_runtime.h>
+#include <sys/stat.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -45,11 +47,13 @@ template <typename T>
 struct DevArray {
     T* d = nullptr;
     size_t n = 0;
-    cudaError_t alloc(size_t count)
+    // The zero fill runs on the legacy default stream and is NOT ordered against the engine's non-blocking streams:
+    // callers that launch work right after an allocation follow it with sync_legacy_stream() (engine_create does once).
+    cudaError_t alloc(size_t count, bool zero = true)
     {
         n = count;
         cudaError_t e = cudaMalloc((void**)&d, std::max<size_t>(count, 1) * sizeof(T));
-        if (e == cudaSuccess) e = cudaMemset(d, 0, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess && zero) e = cudaMemset(d, 0, std::max<size_t>(count, 1) * sizeof(T));
         return e;
     }
     void release() { if (d) cudaFree(d); d = nullptr; n = 0; }
@@ -58,6 +62,9 @@ struct DevArray {
 struct ModelEntry {
     HostModel host;
     float* d_weights = nullptr;
+    std::string cache_key; // path + mtime + size of the file it was parsed from ("" = registered from arrays)
+    int holds = 0;         // ids handed out by aidax_model_load_json / aidax_model_register and not yet released
+    int refs = 0;          // streams bound to it
 };
 
 struct Family {       // one kernel family = (cell, hidden); cell 2 = streams without a network
@@ -109,8 +116,13 @@ struct aidax_engine {
     std::vector<uint32_t> h_flags, h_cmd;
     std::vector<float> h_pre_target, h_master_target, h_p_port, h_p_init, h_cmd_pre_mem, h_cmd_master_mem, h_exp_coef, h_lin_denom;
     std::vector<double> h_bq_coef;
-    bool upload_order = true;    // AIDAX_UPLOAD_ORDER=0 (diagnosis only): let control uploads overlap in-flight kernels, see upload_dirty
     bool any_dirty = false;
+    // Uploads that kernels on OTHER streams consume (weights, the model table, block tables) go through one dedicated
+    // stream and are waited for before the call returns (upload_blocking): a pageable-memory cudaMemcpy on the legacy
+    // stream may return while its DMA is still in flight, and nothing orders that DMA against the engine's non-blocking
+    // kernel streams.
+    std::mutex mu_up;
+    cudaStream_t stream_up = nullptr;
 
     // device arrays
     DevArray<uint32_t> d_flags, d_cmd, d_dflags;
@@ -122,7 +134,7 @@ struct aidax_engine {
     std::vector<int> h_tables;
 
     std::vector<ModelEntry> models;
-    std::map<std::string, int> model_cache;
+    std::map<std::string, int> model_cache; // cache_key -> id, only while the model is held or bound
     bool models_dirty = false;
 
     std::vector<Family> families;
@@ -196,7 +208,8 @@ static void note_param_tracking(aidax_engine* e, int s)
 {
     const StreamHost& sh = e->streams[s];
     if (e->track_flag[s]) return;
-    if (float_not_equal(sh.param_target[0], sh.ctrl[AIDAX_CTRL_PARAM1]) || float_not_equal(sh.param_target[1], sh.ctrl[AIDAX_CTRL_PARAM2])) {
+    if (sh.master_seen != sh.master_target || float_not_equal(sh.param_target[0], sh.ctrl[AIDAX_CTRL_PARAM1]) ||
+        float_not_equal(sh.param_target[1], sh.ctrl[AIDAX_CTRL_PARAM2])) {
         e->track_flag[s] = 1;
         e->track_list.push_back(s);
     }
@@ -239,6 +252,21 @@ static cudaError_t upload_rows(aidax_engine* e, cudaStream_t st, T* dev, const T
 
 static cudaError_t sync_kernel_streams(aidax_engine* e);
 
+// Host -> device copy that has LANDED when the call returns, whatever stream consumes the data afterwards.
+// (AIDAX_LEGACY_UPLOADS restores the round-1 behaviour for the fault-reproduction build only, tools/race_probe.sh.)
+static cudaError_t upload_blocking(aidax_engine* e, void* dst, const void* src, size_t bytes)
+{
+    if (!bytes) return cudaSuccess;
+#ifdef AIDAX_LEGACY_UPLOADS
+    return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+#else
+    std::lock_guard<std::mutex> lk(e->mu_up);
+    cudaError_t err = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e->stream_up);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream_up);
+    return err;
+#endif
+}
+
 static int upload_dirty(aidax_engine* e, int first, int n, cudaStream_t st)
 {
     if (e->models_dirty) {
@@ -248,10 +276,11 @@ static int upload_dirty(aidax_engine* e, int first, int n, cudaStream_t st)
             md[i] = ModelDev{m.d_weights, m.host.desc.in_gain, m.host.desc.out_gain, m.host.desc.in_skip, m.host.desc.input_size};
         }
         if (e->d_models.n < md.size()) {
+            CUDA_TRY(sync_kernel_streams(e)); // launches in flight still read the old table
             e->d_models.release();
-            CUDA_TRY(e->d_models.alloc(std::max<size_t>(md.size() * 2, 64)));
+            CUDA_TRY(e->d_models.alloc(std::max<size_t>(md.size() * 2, 64), /*zero=*/false));
         }
-        CUDA_TRY(cudaMemcpy(e->d_models.d, md.data(), md.size() * sizeof(ModelDev), cudaMemcpyHostToDevice));
+        CUDA_TRY(upload_blocking(e, e->d_models.d, md.data(), md.size() * sizeof(ModelDev)));
         e->models_dirty = false;
     }
     if (!e->any_dirty) return AIDAX_OK;
@@ -268,15 +297,10 @@ static int upload_dirty(aidax_engine* e, int first, int n, cudaStream_t st)
             if ((s < first || s >= last) && (e->dirty_ctrl[s] || e->dirty_coef[s] || e->dirty_cmd[s])) remaining = true;
     }
     e->any_dirty = remaining;
-    // Control uploads of this range must not overlap the kernels of ranges submitted earlier in the same period.
-    // Measured on B200 (tools/c4_probe.py): with the hand-over of a model-binding period streaming (range A's 2048-step
-    // pre-warm kernel still running on its kernel stream while range B's pageable-memory uploads are issued on
-    // another), the FP32 latency shapes of H = 20 fault with "illegal memory access" although the column ranges are
-    // disjoint and compute-sanitizer sees no invalid access when the same work runs serialised; with this wait in
-    // place -- or with one kernel stream -- every mix of models passes.  Page-locking the shadows does not change it, so
-    // it is not the staged pageable copy path.  Root cause not identified yet.
-    // Steady-state periods upload nothing and never get here, so the streaming overlap is unaffected.
-    if (e->upload_order && !e->pending.empty() && (chi > clo || fhi > flo || mhi > mlo)) CUDA_TRY(sync_kernel_streams(e));
+#ifdef AIDAX_LEGACY_UPLOADS
+    if (std::getenv("AIDAX_UPLOAD_ORDER") == nullptr || std::atoi(std::getenv("AIDAX_UPLOAD_ORDER")) != 0)
+        if (!e->pending.empty() && (chi > clo || fhi > flo || mhi > mlo)) CUDA_TRY(sync_kernel_streams(e));
+#endif
     CUDA_TRY(upload_rows(e, st, e->d_flags.d, e->h_flags.data(), 1, clo, chi));
     CUDA_TRY(upload_rows(e, st, e->d_pre_target.d, e->h_pre_target.data(), 1, clo, chi));
     CUDA_TRY(upload_rows(e, st, e->d_master_target.d, e->h_master_target.data(), 1, clo, chi));
@@ -376,11 +400,12 @@ static int build_plan(aidax_engine* e, int first, int n, RangePlan** out)
     if (rp.d_tables.n < e->h_tables.size()) {
         CUDA_TRY(sync_kernel_streams(e));
         rp.d_tables.release();
-        CUDA_TRY(rp.d_tables.alloc(e->h_tables.size() * 2 + 1024));
+        CUDA_TRY(rp.d_tables.alloc(e->h_tables.size() * 2 + 1024, /*zero=*/false));
     }
     if (!e->h_tables.empty()) {
         CUDA_TRY(sync_kernel_streams(e)); // a previous launch may still read the old table
-        CUDA_TRY(cudaMemcpy(rp.d_tables.d, e->h_tables.data(), e->h_tables.size() * sizeof(int), cudaMemcpyHostToDevice));
+        // ... and the launch that follows (on a non-blocking kernel stream) must see the new one: see upload_blocking
+        CUDA_TRY(upload_blocking(e, rp.d_tables.d, e->h_tables.data(), e->h_tables.size() * sizeof(int)));
     }
     rp.epoch = e->membership_epoch;
     rp.tile_mode = e->tile_mode;
@@ -457,9 +482,9 @@ static int launch_all(aidax_engine* e, cudaStream_t st, int first, int n, int n_
     return AIDAX_OK;
 }
 
+// call with e->mu held (n_open_hi and the open flags change under it)
 static int check_stream(aidax_engine* e, int s)
 {
-    if (!e) return fail(AIDAX_ERR_ARG, "null engine");
     if (s < 0 || s >= e->n_open_hi || !e->streams[s].open) return fail(AIDAX_ERR_ARG, "unknown stream %d", s);
     return AIDAX_OK;
 }
@@ -513,6 +538,7 @@ int aidax_engine_create(int device, int max_streams, int max_block, aidax_engine
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_out, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_up, cudaStreamNonBlocking));
     if (const char* v = std::getenv("AIDAX_KERNEL_STREAMS")) e->n_kstreams = std::max(1, std::min(std::atoi(v), (int)aidax_engine::kMaxKernelStreams));
     e->kstream[0] = e->stream;
     for (int k = 1; k < e->n_kstreams; ++k) CUDA_TRY(cudaStreamCreateWithFlags(&e->kstream[k], cudaStreamNonBlocking));
@@ -532,7 +558,6 @@ int aidax_engine_create(int device, int max_streams, int max_block, aidax_engine
     e->h_cmd_pre_mem.assign(cap, 0.f); e->h_cmd_master_mem.assign(cap, 0.f);
     e->h_exp_coef.assign(cap, 0.f); e->h_lin_denom.assign(cap, 4800.f);
     e->h_bq_coef.assign((size_t)kNumBiquads * 5 * cap, 0.0);
-    if (const char* v = std::getenv("AIDAX_UPLOAD_ORDER")) e->upload_order = std::atoi(v) != 0;
     CUDA_TRY(e->d_flags.alloc(cap)); CUDA_TRY(e->d_cmd.alloc(cap)); CUDA_TRY(e->d_dflags.alloc(cap));
     CUDA_TRY(e->d_pre_target.alloc(cap)); CUDA_TRY(e->d_master_target.alloc(cap));
     CUDA_TRY(e->d_p_port.alloc(2 * cap)); CUDA_TRY(e->d_p_init.alloc(2 * cap));
@@ -543,6 +568,7 @@ int aidax_engine_create(int device, int max_streams, int max_block, aidax_engine
     CUDA_TRY(e->d_rnn.alloc((size_t)2 * kMaxHidden * cap));
     CUDA_TRY(e->d_bq_coef.alloc((size_t)kNumBiquads * 5 * cap)); CUDA_TRY(e->d_bq_z.alloc((size_t)kNumBiquads * 2 * cap));
     CUDA_TRY(e->d_io_in.alloc(cap * (size_t)max_block)); CUDA_TRY(e->d_io_out.alloc(cap * (size_t)max_block));
+    CUDA_TRY(cudaDeviceSynchronize()); // the zero fills above ran on the legacy stream; everything else uses non-blocking streams
     collect_families(e.get());
     *out = e.release();
     return AIDAX_OK;
@@ -570,6 +596,7 @@ int aidax_engine_destroy(aidax_engine* e)
     for (int k = 1; k < e->n_kstreams; ++k) if (e->kstream[k]) cudaStreamDestroy(e->kstream[k]);
     if (e->stream_in) cudaStreamDestroy(e->stream_in);
     if (e->stream_out) cudaStreamDestroy(e->stream_out);
+    if (e->stream_up) cudaStreamDestroy(e->stream_up);
     cudaStreamDestroy(e->stream);
     delete e;
     return AIDAX_OK;
@@ -586,18 +613,58 @@ int aidax_engine_configure(aidax_engine* e, int tile_mode, int math_mode)
     return AIDAX_OK;
 }
 
-static int register_host_model(aidax_engine* e, HostModel&& hm, int* id_out)
+// Packs the weights and puts them on the device WITHOUT the engine lock (parsing, packing, cudaMalloc and the copy may
+// take milliseconds and run on the LV2 worker thread; every instance's audio-thread run() takes e->mu), then takes
+// the lock only to append the entry.  The returned id is held (see aidax_model_release).
+static int register_host_model(aidax_engine* e, HostModel&& hm, const std::string& cache_key, int* id_out)
 {
     const std::vector<float> packed = pack_model(hm);
     ModelEntry me;
     CUDA_TRY(cudaSetDevice(e->device));
     CUDA_TRY(cudaMalloc((void**)&me.d_weights, packed.size() * sizeof(float)));
-    CUDA_TRY(cudaMemcpy(me.d_weights, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+    const cudaError_t err = upload_blocking(e, me.d_weights, packed.data(), packed.size() * sizeof(float));
+    if (err != cudaSuccess) {
+        cudaFree(me.d_weights);
+        return fail(AIDAX_ERR_CUDA, "weight upload failed: %s", cudaGetErrorString(err));
+    }
     me.host = std::move(hm);
+    me.cache_key = cache_key;
+    me.holds = 1;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!cache_key.empty()) {
+        // another thread may have loaded the same file meanwhile: keep one copy
+        auto it = e->model_cache.find(cache_key);
+        if (it != e->model_cache.end()) {
+            cudaFree(me.d_weights);
+            e->models[it->second].holds++;
+            if (id_out) *id_out = it->second;
+            return AIDAX_OK;
+        }
+    }
     e->models.push_back(std::move(me));
     e->models_dirty = true;
-    if (id_out) *id_out = (int)e->models.size() - 1;
+    const int id = (int)e->models.size() - 1;
+    if (!cache_key.empty()) e->model_cache[cache_key] = id;
+    if (id_out) *id_out = id;
     return AIDAX_OK;
+}
+
+// Drops the device weights of a model nobody holds or is bound to (call with e->mu held).  The pointer is returned so
+// that the caller frees it after unlocking: cudaFree waits for the device, and in-flight kernels may still read it.
+static float* retire_model_locked(aidax_engine* e, int id)
+{
+    ModelEntry& m = e->models[id];
+    if (m.holds > 0 || m.refs > 0 || !m.d_weights) return nullptr;
+    float* w = m.d_weights;
+    m.d_weights = nullptr;
+    if (!m.cache_key.empty()) {
+        auto it = e->model_cache.find(m.cache_key);
+        if (it != e->model_cache.end() && it->second == id) e->model_cache.erase(it);
+    }
+    m.host.W.clear(); m.host.U.clear(); m.host.b.clear(); m.host.dense_w.clear();
+    m.host.W.shrink_to_fit(); m.host.U.shrink_to_fit();
+    e->models_dirty = true;
+    return w;
 }
 
 int aidax_model_register(aidax_engine* e, const aidax_model_desc* desc, const float* W, const float* U, const float* b,
@@ -616,31 +683,67 @@ int aidax_model_register(aidax_engine* e, const aidax_model_desc* desc, const fl
     hm.b.assign(b, b + (size_t)(desc->cell == AIDAX_CELL_LSTM ? 4 * H : 6 * H));
     hm.dense_w.assign(dense_w, dense_w + H);
     hm.dense_b = dense_b;
-    std::lock_guard<std::mutex> lk(e->mu);
-    return register_host_model(e, std::move(hm), model_id_out);
+    return register_host_model(e, std::move(hm), std::string(), model_id_out);
+}
+
+// The reference re-reads the file on every patch:Set (loadModelFromPath, rt-neural-generic.cpp:963-1013).  Here a
+// file is parsed once per (path, modification time, size) while some instance still holds or runs the result, so
+// that N instances loading one capture share one weight block -- and a capture re-exported to the same path is read
+// again.
+static std::string model_cache_key(const char* path)
+{
+    struct stat st;
+    if (stat(path, &st) != 0) return std::string();
+    char buf[96];
+    snprintf(buf, sizeof(buf), "|%lld.%09ld|%lld", (long long)st.st_mtim.tv_sec, (long)st.st_mtim.tv_nsec, (long long)st.st_size);
+    return std::string(path) + buf;
 }
 
 int aidax_model_load_json(aidax_engine* e, const char* path, int* model_id_out, int* input_size_out)
 {
     if (!e || !path) return fail(AIDAX_ERR_ARG, "null argument");
-    std::lock_guard<std::mutex> lk(e->mu);
-    auto it = e->model_cache.find(path);
+    const std::string key = model_cache_key(path);
     int id = -1;
-    if (it != e->model_cache.end()) {
-        id = it->second;
-    } else {
+    if (!key.empty()) {
+        std::lock_guard<std::mutex> lk(e->mu);
+        auto it = e->model_cache.find(key);
+        if (it != e->model_cache.end()) {
+            id = it->second;
+            e->models[id].holds++;
+        }
+    }
+    if (id < 0) {
         HostModel hm;
         try {
             hm = load_model_file(path);
         } catch (const std::exception& ex) {
             return fail(AIDAX_ERR_MODEL, "Unable to load json file: %s Error: %s", path, ex.what());
         }
-        const int rc = register_host_model(e, std::move(hm), &id);
+        const int rc = register_host_model(e, std::move(hm), key, &id);
         if (rc) return rc;
-        e->model_cache[path] = id;
     }
+    std::lock_guard<std::mutex> lk(e->mu);
     if (model_id_out) *model_id_out = id;
     if (input_size_out) *input_size_out = e->models[id].host.desc.input_size;
+    return AIDAX_OK;
+}
+
+int aidax_model_release(aidax_engine* e, int model_id)
+{
+    if (!e) return fail(AIDAX_ERR_ARG, "null engine");
+    float* dead = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        if (model_id < 0 || model_id >= (int)e->models.size()) return fail(AIDAX_ERR_ARG, "unknown model %d", model_id);
+        ModelEntry& m = e->models[model_id];
+        if (m.holds <= 0) return fail(AIDAX_ERR_STATE, "model %d is not held", model_id);
+        m.holds--;
+        dead = retire_model_locked(e, model_id);
+    }
+    if (dead) {
+        cudaSetDevice(e->device);
+        cudaFree(dead);
+    }
     return AIDAX_OK;
 }
 
@@ -724,24 +827,35 @@ int aidax_stream_open(aidax_engine* e, double sample_rate, int* stream_id_out)
 
 int aidax_stream_close(aidax_engine* e, int stream)
 {
-    int rc = check_stream(e, stream);
-    if (rc) return rc;
-    std::lock_guard<std::mutex> lk(e->mu);
-    e->streams[stream].open = false;
-    e->streams[stream].model = -1;
-    e->membership_epoch++;
+    if (!e) return fail(AIDAX_ERR_ARG, "null engine");
+    float* dead = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        int rc = check_stream(e, stream);
+        if (rc) return rc;
+        StreamHost& sh = e->streams[stream];
+        if (sh.model >= 0 && --e->models[sh.model].refs == 0) dead = retire_model_locked(e, sh.model);
+        sh.open = false;
+        sh.model = -1;
+        e->membership_epoch++;
+    }
+    if (dead) {
+        cudaSetDevice(e->device);
+        cudaFree(dead); // waits for the device: launches in flight may still read the block
+    }
     return AIDAX_OK;
 }
 
 int aidax_stream_activate(aidax_engine* e, int stream)
 {
+    if (!e) return fail(AIDAX_ERR_ARG, "null engine");
+    std::lock_guard<std::mutex> lk(e->mu);
     int rc = check_stream(e, stream);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(e->mu);
     StreamHost& sh = e->streams[stream];
     e->h_cmd[stream] |= C_SET_GAIN_MEMS | (sh.model >= 0 ? C_FIRST_RUN : 0u);
     e->h_cmd_pre_mem[stream] = sh.pre_target;
-    e->h_cmd_master_mem[stream] = sh.master_target;
+    e->h_cmd_master_mem[stream] = sh.master_seen;
     e->dirty_cmd[stream] = 1;
     e->any_dirty = true;
     return AIDAX_OK;
@@ -749,44 +863,57 @@ int aidax_stream_activate(aidax_engine* e, int stream)
 
 int aidax_stream_set_model(aidax_engine* e, int stream, int model_id, float old_param1, float old_param2)
 {
-    int rc = check_stream(e, stream);
-    if (rc) return rc;
-    std::lock_guard<std::mutex> lk(e->mu);
-    if (model_id >= (int)e->models.size()) return fail(AIDAX_ERR_ARG, "unknown model %d", model_id);
-    StreamHost& sh = e->streams[stream];
-    sh.model = model_id < 0 ? -1 : model_id;
-    if (model_id >= 0) {
-        const aidax_model_desc& d = e->models[model_id].host.desc;
-        e->h_lin_denom[stream] = 0.1f * d.samplerate;
-        e->h_p_init[stream] = old_param1;
-        e->h_p_init[(size_t)e->cap + stream] = old_param2;
-        e->h_cmd[stream] |= C_SET_MODEL;
-        e->dirty_cmd[stream] = 1;
-        // the new model's smoother targets, as setTargetValue would leave them (ValueSmoother.hpp:209-216)
-        sh.param_target[0] = float_not_equal(0.f, old_param1) ? old_param1 : 0.f;
-        sh.param_target[1] = float_not_equal(0.f, old_param2) ? old_param2 : 0.f;
+    if (!e) return fail(AIDAX_ERR_ARG, "null engine");
+    float* dead = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        int rc = check_stream(e, stream);
+        if (rc) return rc;
+        if (model_id >= (int)e->models.size()) return fail(AIDAX_ERR_ARG, "unknown model %d", model_id);
+        if (model_id >= 0 && !e->models[model_id].d_weights) return fail(AIDAX_ERR_STATE, "model %d was released", model_id);
+        StreamHost& sh = e->streams[stream];
+        const int old_model = sh.model;
+        sh.model = model_id < 0 ? -1 : model_id;
+        if (sh.model >= 0) e->models[sh.model].refs++;
+        if (old_model >= 0 && --e->models[old_model].refs == 0) dead = retire_model_locked(e, old_model);
+        if (model_id >= 0) {
+            const aidax_model_desc& d = e->models[model_id].host.desc;
+            e->h_lin_denom[stream] = 0.1f * d.samplerate;
+            e->h_p_init[stream] = old_param1;
+            e->h_p_init[(size_t)e->cap + stream] = old_param2;
+            e->h_cmd[stream] |= C_SET_MODEL;
+            e->dirty_cmd[stream] = 1;
+            // the new model's smoother targets, as setTargetValue would leave them (ValueSmoother.hpp:209-216)
+            sh.param_target[0] = float_not_equal(0.f, old_param1) ? old_param1 : 0.f;
+            sh.param_target[1] = float_not_equal(0.f, old_param2) ? old_param2 : 0.f;
+        }
+        // F_NET depends on the binding
+        if (sh.have_ctrl) decode_controls(sh, sh.ctrl, sh.loading, sh.model >= 0);
+        else {
+            float c[AIDAX_N_CONTROLS];
+            std::memcpy(c, sh.ctrl, sizeof(c));
+            const float pt = sh.pre_target, mt = sh.master_target;
+            decode_controls(sh, c, sh.loading, sh.model >= 0);
+            sh.have_ctrl = false; sh.pre_target = pt; sh.master_target = mt;
+        }
+        sync_stream_shadow(e, stream);
+        e->any_dirty = true;
+        e->membership_epoch++;
     }
-    // F_NET depends on the binding
-    if (sh.have_ctrl) decode_controls(sh, sh.ctrl, sh.loading, sh.model >= 0);
-    else {
-        float c[AIDAX_N_CONTROLS];
-        std::memcpy(c, sh.ctrl, sizeof(c));
-        const float pt = sh.pre_target, mt = sh.master_target;
-        decode_controls(sh, c, sh.loading, sh.model >= 0);
-        sh.have_ctrl = false; sh.pre_target = pt; sh.master_target = mt;
+    if (dead) {
+        cudaSetDevice(e->device);
+        cudaFree(dead);
     }
-    sync_stream_shadow(e, stream);
-    e->any_dirty = true;
-    e->membership_epoch++;
     return AIDAX_OK;
 }
 
 int aidax_stream_set_controls(aidax_engine* e, int stream, const float controls[AIDAX_N_CONTROLS], int loading)
 {
-    int rc = check_stream(e, stream);
-    if (rc) return rc;
+    if (!e) return fail(AIDAX_ERR_ARG, "null engine");
     if (!controls) return fail(AIDAX_ERR_ARG, "null controls");
     std::lock_guard<std::mutex> lk(e->mu);
+    int rc = check_stream(e, stream);
+    if (rc) return rc;
     StreamHost& sh = e->streams[stream];
     const uint32_t redesigned = decode_controls(sh, controls, loading != 0, sh.model >= 0);
     if (redesigned) write_coefs(e, stream, redesigned);
@@ -812,9 +939,10 @@ int aidax_streams_set_params(aidax_engine* e, int first_stream, int n, const flo
 
 int aidax_stream_get_params(aidax_engine* e, int stream, float* target1, float* target2)
 {
+    if (!e) return fail(AIDAX_ERR_ARG, "null engine");
+    std::lock_guard<std::mutex> lk(e->mu);
     int rc = check_stream(e, stream);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(e->mu);
     const StreamHost& sh = e->streams[stream];
     if (target1) *target1 = sh.model >= 0 ? sh.param_target[0] : 0.f;
     if (target2) *target2 = sh.model >= 0 ? sh.param_target[1] : 0.f;
@@ -823,9 +951,10 @@ int aidax_stream_get_params(aidax_engine* e, int stream, float* target1, float* 
 
 int aidax_stream_get_state(aidax_engine* e, int stream, float* h, float* c, double* biquad_z)
 {
+    if (!e) return fail(AIDAX_ERR_ARG, "null engine");
+    std::lock_guard<std::mutex> lk(e->mu);
     int rc = check_stream(e, stream);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(e->mu);
     CUDA_TRY(cudaSetDevice(e->device));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     const StreamHost& sh = e->streams[stream];
@@ -842,9 +971,10 @@ int aidax_stream_get_state(aidax_engine* e, int stream, float* h, float* c, doub
 
 int aidax_stream_set_state(aidax_engine* e, int stream, const float* h, const float* c, const double* biquad_z)
 {
+    if (!e) return fail(AIDAX_ERR_ARG, "null engine");
+    std::lock_guard<std::mutex> lk(e->mu);
     int rc = check_stream(e, stream);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(e->mu);
     CUDA_TRY(cudaSetDevice(e->device));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     const StreamHost& sh = e->streams[stream];
@@ -876,7 +1006,7 @@ static void after_render(aidax_engine* e, int first, int n, int n_samples)
     for (size_t i = 0; i < e->track_list.size(); ++i) {
         const int s = e->track_list[i];
         if (s < first || s >= last) { e->track_list[keep++] = s; continue; }
-        if (e->streams[s].open) track_param_targets(e->streams[s], n_samples);
+        if (e->streams[s].open) track_run_targets(e->streams[s], n_samples);
         e->track_flag[s] = 0; // any later change of the ports, flags or model re-lists the stream
     }
     e->track_list.resize(keep);
@@ -1199,5 +1329,13 @@ int aidax_measure_pcie(int device, size_t bytes, double gbs_out[3])
 }
 
 uint64_t aidax_engine_launch_count(aidax_engine* e) { return e ? e->launches : 0; }
+
+int aidax_engine_pci_bus_id(aidax_engine* e, char* out, int cap)
+{
+    if (!e || !out || cap < 13) return fail(AIDAX_ERR_ARG, "bad pci_bus_id arguments");
+    CUDA_TRY(cudaDeviceGetPCIBusId(out, cap, e->device));
+    for (char* c = out; *c; ++c) *c = (char)tolower(*c); // sysfs spells bus ids in lower case
+    return AIDAX_OK;
+}
 
 } // extern "C"

@@ -46,25 +46,46 @@ struct WorkerLoadMessage { WorkerMessageType type; char path[1024]; };
 struct LoadedModel { int model_id; int input_size; char* path; float old_param1, old_param2; };
 struct WorkerApplyMessage { WorkerMessageType type; LoadedModel* model; };
 
+struct Plugin;
+
 // ---------------------------------------------------------------------------- process-wide engine
+// Per-stream facts the per-period code needs live in structure-of-arrays tables indexed by the stream id, and the
+// Plugin objects themselves sit in one pool indexed the same way (handle == pool + stream): with hundreds of thousands
+// of instances per period the host side is bound by memory traffic, and the bulk entry (run_block) must not touch a
+// plugin object at all on an ordinary period.
+enum : uint8_t {
+    ST_LIVE = 1,     // an instance owns this stream id
+    ST_FAST_OK = 2,  // controls latched with the current `loading` state and both audio ports connected: an unchanged
+                     // control row means this period needs no control-rate work
+};
+constexpr int kLatchPitch = 24; // floats per latched row: the 21 control values ([19] = ModelInSize as last written), 32-byte aligned rows
+
 struct EngineHub {
     std::mutex mu;
     aidax_engine* engine = nullptr;
     int max_instances = 0, max_block = 0, device = -1;
     int refs = 0;
-    // batch state: run() parks its ports in the slot of its own stream (no lock: every instance owns one
-    // slot, begin()/end() are called by the host while no run() is in flight), end() walks the slots in order
+    size_t cap = 0;                       // entries in the per-stream tables
+    Plugin* pool = nullptr;               // [cap], constructed on instantiate
+    std::vector<uint8_t> st_flags;        // ST_*
+    std::vector<const float*> st_in;      // audio ports
+    std::vector<float*> st_out;
+    std::vector<float*> st_ctl;           // control ports 4..24 as one row, or nullptr when they are scattered
+    std::vector<const void*> st_evt;      // CONTROL atom port
+    std::vector<uint32_t> st_ran;         // period (epoch) in which the instance last took part in a batch
+    float* latched = nullptr;             // [cap][kLatchPitch]
+    std::atomic<uint32_t> port_epoch{1};  // bumped whenever an audio port or the set of live streams changes
+    // batch state: begin()/end() are called by the host while no run() is in flight
     std::atomic<bool> batching{false};
-    struct Pending { int stream; const float* in; float* out; uint32_t n; };
-    struct Slot { const float* in; float* out; uint32_t n; uint32_t epoch; };
-    std::vector<Slot> slots;
     uint32_t epoch = 0;
-    // Streaming hand-over: stream ids are cut into fixed chunks; the run() that parks the last live instance of a
-    // chunk submits that chunk's copy-in / kernels / copy-out at once (aidax_render_host_submit), so the transfers
-    // of early chunks overlap the run() calls of later ones.  end() renders what is left and waits.
-    // Counting is two-level so that run() calls on different host threads do not fight over one cache line: a run()
-    // bumps the counter of its 64-stream block (a host thread works through neighbouring instances, so a block's
-    // line stays in its cache); the run() that fills a block bumps the chunk's counter.
+    std::atomic<uint32_t> period_n{0};    // n_samples of the current period (the first instance to take part sets it)
+    struct Pending { int stream; const float* in; float* out; uint32_t n; };
+    // Streaming hand-over: stream ids are cut into fixed chunks; the run() / run_block() that completes the last live
+    // instance of a chunk submits that chunk's copy-in / kernels / copy-out at once (aidax_render_host_submit), so the
+    // transfers of early chunks overlap the control scan of later ones.  end() renders what is left and waits.
+    // Counting is two-level so that calls on different host threads do not fight over one cache line: taking part
+    // bumps the counter of a 64-stream block (a host thread works through neighbouring instances, so a block's line
+    // stays in its cache; run_block adds a whole block's worth at once); filling a block bumps the chunk's counter.
     static constexpr int kBlockStreams = 64;
     int chunk_streams = 16384;
     struct alignas(64) Block {
@@ -75,6 +96,14 @@ struct EngineHub {
         std::atomic<int> blocks_done{0};  // blocks of this chunk whose live instances have all run in the current batch
         std::atomic<int> blocks_live{0};  // blocks with at least one live instance
         std::atomic<uint32_t> submitted_epoch{0};
+        // where the chunk's audio ports are, worked out once per change of port_epoch (only the thread that completes
+        // the chunk reads or writes this)
+        uint32_t layout_epoch = 0;
+        bool regular = false;   // live streams [first, last) contiguous, ports = rows of two arenas with one stride
+        int first = 0, last = 0;
+        const float* in0 = nullptr;
+        float* out0 = nullptr;
+        ptrdiff_t stride = 0;
     };
     std::unique_ptr<Block[]> blocks;
     std::unique_ptr<Chunk[]> chunks;
@@ -89,6 +118,38 @@ int env_int(const char* name, int dflt)
     return v && *v ? atoi(v) : dflt;
 }
 
+// ---------------------------------------------------------------------------- one plugin instance
+struct alignas(64) Plugin {
+    // ---- touched by every run()
+    const float* in = nullptr;
+    float* out_1 = nullptr;
+    const LV2_Atom_Sequence* control_port = nullptr;
+    LV2_Atom_Sequence* notify_port = nullptr;
+    float* ctl_row = nullptr;        // set when control ports 4..24 are one contiguous float row (what a batch host connects)
+    float* latched = nullptr;        // this stream's row of g_hub.latched
+    aidax_engine* engine = nullptr;
+    int stream = -1;
+    int last_input_size = 0;         // rt-neural-generic.cpp:316
+    uint32_t notify_capacity = 0;    // atom.size of the notify port at the start of the last run() (:528-534)
+    LV2_URID urid_sequence = 0;
+    bool loading = true;             // :318
+    bool latched_valid = false;
+    bool latched_loading = true;
+    bool notify_armed = false;       // a run() has seen both atom ports: work_response may report (the reference's forge.buf != NULL)
+    bool forge_ready = false;        // the forge already points at this period's notify sequence
+    // ---- cold
+    float* ctl[P_COUNT] = {};
+    LV2_URID_Map* map = nullptr;
+    LV2_Worker_Schedule* schedule = nullptr;
+    LV2_Log_Log* log = nullptr;
+    LV2_Log_Logger logger{};
+    LV2_Atom_Forge forge{};
+    LV2_Atom_Forge_Frame notify_frame{};
+    Uris uris{};
+    double samplerate = 48000.0;
+    LoadedModel* model = nullptr;
+};
+
 // Creates the engine on first use.  Sizes: configure() > environment > defaults.
 aidax_engine* hub_engine()
 {
@@ -101,9 +162,24 @@ aidax_engine* hub_engine()
         fprintf(stderr, "rt-neural-generic (aidax): cannot create the CUDA engine: %s\n", aidax_last_error());
         g_hub.engine = nullptr;
     } else {
-        g_hub.slots.assign((size_t)g_hub.max_instances + 32, EngineHub::Slot{nullptr, nullptr, 0u, 0u});
+        const size_t cap = (size_t)g_hub.max_instances + 32; // the engine rounds its capacity up to a multiple of 32
+        g_hub.cap = cap;
+        g_hub.pool = (Plugin*)aligned_alloc(64, sizeof(Plugin) * cap); // pages are touched as instances are created
+        g_hub.latched = (float*)aligned_alloc(64, sizeof(float) * kLatchPitch * cap);
+        if (!g_hub.pool || !g_hub.latched) {
+            fprintf(stderr, "rt-neural-generic (aidax): out of memory for %zu instances\n", cap);
+            aidax_engine_destroy(g_hub.engine);
+            g_hub.engine = nullptr;
+            return nullptr;
+        }
+        g_hub.st_flags.assign(cap, 0);
+        g_hub.st_in.assign(cap, nullptr);
+        g_hub.st_out.assign(cap, nullptr);
+        g_hub.st_ctl.assign(cap, nullptr);
+        g_hub.st_evt.assign(cap, nullptr);
+        g_hub.st_ran.assign(cap, 0u);
         g_hub.chunk_streams = std::max(128, env_int("AIDAX_BATCH_CHUNK", 16384)) & ~127; // whole tiles of every kernel shape
-        g_hub.n_chunks = (int)((g_hub.slots.size() + g_hub.chunk_streams - 1) / g_hub.chunk_streams);
+        g_hub.n_chunks = (int)((cap + g_hub.chunk_streams - 1) / g_hub.chunk_streams);
         g_hub.n_blocks = g_hub.n_chunks * (g_hub.chunk_streams / EngineHub::kBlockStreams);
         g_hub.chunks.reset(new EngineHub::Chunk[g_hub.n_chunks]);
         g_hub.blocks.reset(new EngineHub::Block[g_hub.n_blocks]);
@@ -126,6 +202,7 @@ int batch_begin()
 {
     std::lock_guard<std::mutex> lk(g_hub.mu);
     g_hub.epoch++;
+    g_hub.period_n.store(0, std::memory_order_relaxed);
     g_hub.submit_error.store(0, std::memory_order_relaxed);
     for (int c = 0; c < g_hub.n_chunks; ++c) g_hub.chunks[c].blocks_done.store(0, std::memory_order_relaxed);
     for (int b = 0; b < g_hub.n_blocks; ++b) g_hub.blocks[b].parked.store(0, std::memory_order_relaxed);
@@ -135,12 +212,12 @@ int batch_begin()
 
 // Renders a set of deferred run() calls with as few engine calls as possible: runs of consecutive
 // stream ids whose port buffers are rows of one arena (constant stride) go straight from the
-// caller's memory; anything else is gathered through pinned staging rows.
+// caller's memory; anything else is rendered stream by stream.
 int render_pending(std::vector<EngineHub::Pending>& items)
 {
     aidax_engine* e = g_hub.engine;
     if (!e || items.empty()) return 0;
-    // items arrive sorted by stream id (batch_end walks the slot table in order)
+    // items arrive sorted by stream id (batch_end walks the stream tables in order)
     size_t i = 0;
     while (i < items.size()) {
         const EngineHub::Pending& a = items[i];
@@ -170,31 +247,60 @@ int render_pending(std::vector<EngineHub::Pending>& items)
     return 0;
 }
 
-// Called by the run() that completed chunk c (all of its live instances have parked).  If the parked ports are the
-// rows of one arena (the batch host's layout) the chunk goes to the GPU now; anything irregular is left to end().
+// Where the audio ports of chunk c's live streams are (see Chunk).
+void refresh_chunk_layout(EngineHub::Chunk& ch, int c, uint32_t port_epoch)
+{
+    const int lo = c * g_hub.chunk_streams, hi = std::min<int>(lo + g_hub.chunk_streams, (int)g_hub.cap);
+    ch.layout_epoch = port_epoch;
+    ch.regular = false;
+    int first = lo;
+    while (first < hi && !(g_hub.st_flags[first] & ST_LIVE)) ++first; // closed streams at the edges are fine
+    int last = hi;
+    while (last > first && !(g_hub.st_flags[last - 1] & ST_LIVE)) --last;
+    ch.first = first;
+    ch.last = last;
+    if (last - first < 2) return;
+    const float* in0 = g_hub.st_in[first];
+    float* out0 = g_hub.st_out[first];
+    if (!in0 || !out0 || !g_hub.st_in[first + 1]) return;
+    const ptrdiff_t stride = g_hub.st_in[first + 1] - in0;
+    if (stride <= 0) return;
+    for (int s = first; s < last; ++s)
+        if (!(g_hub.st_flags[s] & ST_LIVE) || g_hub.st_in[s] != in0 + (ptrdiff_t)(s - first) * stride || g_hub.st_out[s] != out0 + (ptrdiff_t)(s - first) * stride)
+            return;
+    ch.in0 = in0;
+    ch.out0 = out0;
+    ch.stride = stride;
+    ch.regular = true;
+}
+
+// Called by the run() / run_block() that completed chunk c (all of its live instances take part in the period with the
+// period's n_samples).  If their ports are the rows of one arena (the batch host's layout) the chunk goes to the GPU
+// now; anything irregular is left to end().
 void submit_chunk(int c)
 {
-    const int lo = c * g_hub.chunk_streams, hi = std::min<int>(lo + g_hub.chunk_streams, (int)g_hub.slots.size());
-    const uint32_t epoch = g_hub.epoch;
-    int first = lo;
-    while (first < hi && g_hub.slots[first].epoch != epoch) ++first; // closed streams at the edges are fine
-    int last = hi;
-    while (last > first && g_hub.slots[last - 1].epoch != epoch) --last;
-    if (last - first < 2) return;
-    const EngineHub::Slot& a = g_hub.slots[first];
-    const ptrdiff_t stride = g_hub.slots[first + 1].in - a.in;
-    if (stride < (ptrdiff_t)a.n) return;
-    for (int s = first; s < last; ++s) {
-        const EngineHub::Slot& sl = g_hub.slots[s];
-        if (sl.epoch != epoch || sl.n != a.n || sl.in != a.in + (ptrdiff_t)(s - first) * stride || sl.out != a.out + (ptrdiff_t)(s - first) * stride)
-            return;
-    }
-    const int rc = aidax_render_host_submit(g_hub.engine, first, last - first, (int)a.n, a.in, a.out, AIDAX_LAYOUT_PLANAR, (size_t)stride);
+    EngineHub::Chunk& ch = g_hub.chunks[c];
+    const uint32_t pe = g_hub.port_epoch.load(std::memory_order_acquire);
+    if (ch.layout_epoch != pe) refresh_chunk_layout(ch, c, pe);
+    const uint32_t n = g_hub.period_n.load(std::memory_order_relaxed);
+    if (!ch.regular || n == 0 || ch.stride < (ptrdiff_t)n) return;
+    const int rc = aidax_render_host_submit(g_hub.engine, ch.first, ch.last - ch.first, (int)n, ch.in0, ch.out0, AIDAX_LAYOUT_PLANAR, (size_t)ch.stride);
     if (rc != AIDAX_OK) {
         g_hub.submit_error.store(rc, std::memory_order_relaxed);
         return;
     }
-    g_hub.chunks[c].submitted_epoch.store(epoch, std::memory_order_release);
+    ch.submitted_epoch.store(g_hub.epoch, std::memory_order_release);
+}
+
+// `k` instances of 64-stream block b have joined the current period
+inline void park_in_block(int b, int k)
+{
+    EngineHub::Block& bl = g_hub.blocks[b];
+    if (bl.parked.fetch_add(k, std::memory_order_acq_rel) + k == bl.live.load(std::memory_order_relaxed)) {
+        const int c = b / (g_hub.chunk_streams / EngineHub::kBlockStreams);
+        EngineHub::Chunk& ch = g_hub.chunks[c];
+        if (ch.blocks_done.fetch_add(1, std::memory_order_acq_rel) + 1 == ch.blocks_live.load(std::memory_order_relaxed)) submit_chunk(c);
+    }
 }
 
 int batch_end()
@@ -204,16 +310,15 @@ int batch_end()
     {
         std::lock_guard<std::mutex> lk(g_hub.mu);
         g_hub.batching.store(false, std::memory_order_release);
-        const int n_slots = (int)g_hub.slots.size(), per_chunk = g_hub.chunk_streams / EngineHub::kBlockStreams;
+        const uint32_t n = g_hub.period_n.load(std::memory_order_relaxed);
+        const int n_slots = (int)g_hub.cap, per_chunk = g_hub.chunk_streams / EngineHub::kBlockStreams;
         for (int c = 0; c < g_hub.n_chunks; ++c) {
             if (g_hub.chunks[c].submitted_epoch.load(std::memory_order_acquire) == g_hub.epoch) continue; // already on the GPU
             for (int b = c * per_chunk; b < (c + 1) * per_chunk; ++b) {
                 if (g_hub.blocks[b].parked.load(std::memory_order_acquire) == 0) continue;
                 const int s1 = std::min(n_slots, (b + 1) * EngineHub::kBlockStreams);
-                for (int s = b * EngineHub::kBlockStreams; s < s1; ++s) {
-                    const EngineHub::Slot& sl = g_hub.slots[s];
-                    if (sl.epoch == g_hub.epoch) items.push_back(EngineHub::Pending{s, sl.in, sl.out, sl.n});
-                }
+                for (int s = b * EngineHub::kBlockStreams; s < s1; ++s)
+                    if (g_hub.st_ran[s] == g_hub.epoch) items.push_back(EngineHub::Pending{s, g_hub.st_in[s], g_hub.st_out[s], n});
             }
         }
     }
@@ -226,42 +331,69 @@ int batch_end()
 
 uint64_t batch_launch_count() { return g_hub.engine ? aidax_engine_launch_count(g_hub.engine) : 0; }
 
+int batch_device_pci_bus_id(char* out, int cap)
+{
+    if (!g_hub.engine || !out || cap <= 0) return 1;
+    return aidax_engine_pci_bus_id(g_hub.engine, out, cap);
+}
+
+void run(LV2_Handle instance, uint32_t n_samples);
+
+// AidaxBatchInterface::run_block (include/aidax_batch.h)
+int batch_run_block(void* const* handles, uint32_t count, uint32_t n_samples)
+{
+    EngineHub& H = g_hub;
+    bool bulk = n_samples != 0 && H.batching.load(std::memory_order_acquire);
+    if (bulk) {
+        uint32_t pn = H.period_n.load(std::memory_order_relaxed);
+        if (pn == 0 && !H.period_n.compare_exchange_strong(pn, n_samples, std::memory_order_relaxed)) pn = H.period_n.load(std::memory_order_relaxed);
+        bulk = H.period_n.load(std::memory_order_relaxed) == n_samples;
+    }
+    if (!bulk) {
+        for (uint32_t i = 0; i < count; ++i) run(handles[i], n_samples);
+        return 0;
+    }
+    const uint32_t epoch = H.epoch;
+    const uint8_t* flags = H.st_flags.data();
+    float* const* ctl = H.st_ctl.data();
+    const void* const* evt = H.st_evt.data();
+    uint32_t* ran = H.st_ran.data();
+    const void* evt_seen = nullptr;
+    bool evt_empty = true;
+    int blk = -1, blk_count = 0;
+    for (uint32_t i = 0; i < count; ++i) {
+        Plugin* p = (Plugin*)handles[i];
+        const size_t s = (size_t)(p - H.pool);
+        bool fast = s < H.cap && (flags[s] & ST_FAST_OK) != 0;
+        if (fast) {
+            const void* ev = evt[s];
+            if (ev != evt_seen) { // idle instances of a batch host share one empty sequence: one look per run of equal pointers
+                evt_seen = ev;
+                evt_empty = !ev || ((const LV2_Atom_Sequence*)ev)->atom.size <= sizeof(LV2_Atom_Sequence_Body);
+            }
+            fast = evt_empty && memcmp(ctl[s], H.latched + s * kLatchPitch, sizeof(float) * AIDAX_N_CONTROLS) == 0;
+        }
+        if (!fast) {
+            if (blk_count) { park_in_block(blk, blk_count); blk_count = 0; }
+            run(p, n_samples);
+            continue;
+        }
+        ran[s] = epoch;
+        const int b = (int)(s / EngineHub::kBlockStreams);
+        if (b != blk) {
+            if (blk_count) park_in_block(blk, blk_count);
+            blk = b;
+            blk_count = 0;
+        }
+        ++blk_count;
+    }
+    if (blk_count) park_in_block(blk, blk_count);
+    return 0;
+}
+
 const AidaxBatchInterface g_batch_iface = {
     AIDAX_BATCH_ABI_VERSION, batch_configure, aidax_host_alloc, aidax_host_free, batch_begin, batch_end, batch_launch_count, aidax_last_error,
-};
-
-// ---------------------------------------------------------------------------- one plugin instance
-// The fields run() touches on an ordinary period (no atom events, no control change) sit in the first three
-// cache lines: with hundreds of thousands of instances per period run() is bound by host memory traffic.
-struct alignas(64) Plugin {
-    // ---- hot
-    const float* in = nullptr;
-    float* out_1 = nullptr;
-    const LV2_Atom_Sequence* control_port = nullptr;
-    LV2_Atom_Sequence* notify_port = nullptr;
-    float* ctl_row = nullptr;        // set when control ports 4..24 are one contiguous float row (what a batch host connects)
-    aidax_engine* engine = nullptr;
-    int stream = -1;
-    int last_input_size = 0;         // rt-neural-generic.cpp:316
-    uint32_t notify_capacity = 0;    // atom.size of the notify port at the start of the last run() (:528-534)
-    LV2_URID urid_sequence = 0;
-    bool loading = true;             // :318
-    bool latched_valid = false;
-    bool latched_loading = true;
-    bool notify_armed = false;       // a run() has seen both atom ports: work_response may report (the reference's forge.buf != NULL)
-    bool forge_ready = false;        // the forge already points at this period's notify sequence
-    float latched[AIDAX_N_CONTROLS];
-    // ---- cold
-    float* ctl[P_COUNT] = {};
-    LV2_URID_Map* map = nullptr;
-    LV2_Worker_Schedule* schedule = nullptr;
-    LV2_Log_Log* log = nullptr;
-    LV2_Log_Logger logger{};
-    LV2_Atom_Forge forge{};
-    LV2_Atom_Forge_Frame notify_frame{};
-    Uris uris{};
-    double samplerate = 48000.0;
-    LoadedModel* model = nullptr;
+    batch_run_block, batch_device_pci_bus_id,
 };
 
 // Points the forge at the notify port and opens the sequence, as run() does at :528-534.
@@ -290,11 +422,19 @@ void map_uris(LV2_URID_Map* map, Uris* u)
     u->patch_value = map->map(map->handle, LV2_PATCH__value);
 }
 
-void free_loaded(LoadedModel* m)
+// freeModel, rt-neural-generic.cpp:1093-1101
+void free_loaded(aidax_engine* e, LoadedModel* m)
 {
     if (!m) return;
+    if (e && m->model_id >= 0) aidax_model_release(e, m->model_id); // streams still bound keep the weights alive
     free(m->path);
     delete m;
+}
+
+inline void set_fast_ok(const Plugin* self, bool ok)
+{
+    uint8_t& f = g_hub.st_flags[self->stream];
+    f = ok ? (uint8_t)(f | ST_FAST_OK) : (uint8_t)(f & ~ST_FAST_OK);
 }
 
 // ---------------------------------------------------------------------------- LV2 callbacks
@@ -302,40 +442,57 @@ void free_loaded(LoadedModel* m)
 // rt-neural-generic.cpp:244-333
 LV2_Handle instantiate(const LV2_Descriptor*, double samplerate, const char*, const LV2_Feature* const* features)
 {
-    Plugin* self = new Plugin();
-    self->samplerate = samplerate;
+    LV2_URID_Map* map = nullptr;
+    LV2_Worker_Schedule* schedule = nullptr;
+    LV2_Log_Log* log = nullptr;
     for (int i = 0; features && features[i]; ++i) {
-        if (!strcmp(features[i]->URI, LV2_URID__map)) self->map = (LV2_URID_Map*)features[i]->data;
-        else if (!strcmp(features[i]->URI, LV2_WORKER__schedule)) self->schedule = (LV2_Worker_Schedule*)features[i]->data;
-        else if (!strcmp(features[i]->URI, LV2_LOG__log)) self->log = (LV2_Log_Log*)features[i]->data;
+        if (!strcmp(features[i]->URI, LV2_URID__map)) map = (LV2_URID_Map*)features[i]->data;
+        else if (!strcmp(features[i]->URI, LV2_WORKER__schedule)) schedule = (LV2_Worker_Schedule*)features[i]->data;
+        else if (!strcmp(features[i]->URI, LV2_LOG__log)) log = (LV2_Log_Log*)features[i]->data;
     }
-    if (!self->map) {
+    if (!map) {
         fprintf(stderr, "Error! Missing feature urid:map %s %d\n", __func__, __LINE__);
-        delete self;
         return nullptr;
     }
-    if (!self->schedule) {
+    if (!schedule) {
         fprintf(stderr, "Error! Missing feature work:schedule %s %d\n", __func__, __LINE__);
-        delete self;
         return nullptr;
     }
+    aidax_engine* engine = hub_engine();
+    int stream = -1;
+    if (!engine || aidax_stream_open(engine, samplerate, &stream) != AIDAX_OK || (size_t)stream >= g_hub.cap) {
+        // No CPU fallback: without the CUDA engine the plugin cannot exist.
+        LV2_Log_Logger lg{};
+        lv2_log_logger_init(&lg, map, log);
+        lv2_log_error(&lg, "aidax engine unavailable: %s\n", aidax_last_error());
+        if (engine && stream >= 0) aidax_stream_close(engine, stream);
+        return nullptr;
+    }
+    Plugin* self = new (g_hub.pool + stream) Plugin(); // the handle encodes the stream id
+    self->samplerate = samplerate;
+    self->map = map;
+    self->schedule = schedule;
+    self->log = log;
     map_uris(self->map, &self->uris);
     lv2_log_logger_init(&self->logger, self->map, self->log);
     lv2_atom_forge_init(&self->forge, self->map);
     self->urid_sequence = self->uris.atom_Sequence;
-
-    self->engine = hub_engine();
-    if (!self->engine || aidax_stream_open(self->engine, samplerate, &self->stream) != AIDAX_OK) {
-        // No CPU fallback: without the CUDA engine the plugin cannot exist.
-        lv2_log_error(&self->logger, "aidax engine unavailable: %s\n", aidax_last_error());
-        delete self;
-        return nullptr;
-    }
+    self->engine = engine;
+    self->stream = stream;
+    self->latched = g_hub.latched + (size_t)stream * kLatchPitch;
+    memset(self->latched, 0, sizeof(float) * kLatchPitch);
     {
         std::lock_guard<std::mutex> lk(g_hub.mu);
         g_hub.refs++;
-        if (g_hub.blocks[self->stream / EngineHub::kBlockStreams].live.fetch_add(1) == 0)
-            g_hub.chunks[self->stream / g_hub.chunk_streams].blocks_live.fetch_add(1);
+        g_hub.st_flags[stream] = ST_LIVE;
+        g_hub.st_in[stream] = nullptr;
+        g_hub.st_out[stream] = nullptr;
+        g_hub.st_ctl[stream] = nullptr;
+        g_hub.st_evt[stream] = nullptr;
+        g_hub.st_ran[stream] = 0;
+        g_hub.port_epoch.fetch_add(1, std::memory_order_acq_rel);
+        if (g_hub.blocks[stream / EngineHub::kBlockStreams].live.fetch_add(1) == 0)
+            g_hub.chunks[stream / g_hub.chunk_streams].blocks_live.fetch_add(1);
     }
     self->loading = true;
     self->last_input_size = 0;
@@ -347,17 +504,40 @@ LV2_Handle instantiate(const LV2_Descriptor*, double samplerate, const char*, co
 void connect_port(LV2_Handle instance, uint32_t port, void* data)
 {
     Plugin* self = (Plugin*)instance;
+    const int s = self->stream;
     switch (port) {
-    case P_IN: self->in = (const float*)data; break;
-    case P_OUT_1: self->out_1 = (float*)data; break;
-    case P_CONTROL: self->control_port = (const LV2_Atom_Sequence*)data; break;
-    case P_NOTIFY: self->notify_port = (LV2_Atom_Sequence*)data; break;
+    case P_IN:
+        if (self->in != (const float*)data) {
+            self->in = (const float*)data;
+            g_hub.st_in[s] = self->in;
+            g_hub.port_epoch.fetch_add(1, std::memory_order_acq_rel);
+            if (!self->in) set_fast_ok(self, false);
+        }
+        break;
+    case P_OUT_1:
+        if (self->out_1 != (float*)data) {
+            self->out_1 = (float*)data;
+            g_hub.st_out[s] = self->out_1;
+            g_hub.port_epoch.fetch_add(1, std::memory_order_acq_rel);
+            if (!self->out_1) set_fast_ok(self, false);
+        }
+        break;
+    case P_CONTROL:
+        self->control_port = (const LV2_Atom_Sequence*)data;
+        g_hub.st_evt[s] = data;
+        break;
+    case P_NOTIFY:
+        self->notify_port = (LV2_Atom_Sequence*)data;
+        set_fast_ok(self, false); // the next run() reads the new port's capacity
+        break;
     default:
         if (port < P_COUNT) {
             self->ctl[port] = (float*)data;
             bool row = self->ctl[P_IN_LPF] != nullptr;
             for (uint32_t q = P_IN_LPF; row && q < P_COUNT; ++q) row = self->ctl[q] == self->ctl[P_IN_LPF] + (q - P_IN_LPF);
             self->ctl_row = row ? self->ctl[P_IN_LPF] : nullptr;
+            g_hub.st_ctl[s] = self->ctl_row;
+            set_fast_ok(self, false); // re-latched by the next run()
         }
         break;
     }
@@ -378,12 +558,13 @@ void run(LV2_Handle instance, uint32_t n_samples)
     Plugin* self = (Plugin*)instance;
     const Uris* uris = &self->uris; // (only read when the control port carries events)
 
-    // control ports -> engine (only when something changed; the decode itself mirrors :489-517)
+    // control ports -> engine (only when something changed; the decode itself mirrors :489-517).  Slot
+    // [AIDAX_CTRL_MODELINSIZE] of the row is the ModelInSize OUTPUT port: it carries what this run() writes there
+    // (:518), so that "row == latched row" also says the port already shows the current input size.
     float c[AIDAX_N_CONTROLS];
     if (self->ctl_row) {
         memcpy(c, self->ctl_row, sizeof(c));
-        c[AIDAX_CTRL_MODELINSIZE] = 0.f;
-        // :518; stores that would not change memory are skipped throughout the ordinary-period path: a written line
+        // stores that would not change memory are skipped throughout the ordinary-period path: a written line
         // costs a write-back, and with ~400k instances per period run() is bound by host memory traffic
         if (self->ctl_row[AIDAX_CTRL_MODELINSIZE] != (float)self->last_input_size) self->ctl_row[AIDAX_CTRL_MODELINSIZE] = (float)self->last_input_size;
     } else {
@@ -393,6 +574,7 @@ void run(LV2_Handle instance, uint32_t n_samples)
         }
         if (self->ctl[P_INPUT_SIZE]) *self->ctl[P_INPUT_SIZE] = (float)self->last_input_size; // :518
     }
+    c[AIDAX_CTRL_MODELINSIZE] = (float)self->last_input_size;
 
     // atom messages (:526-586)
     if (self->notify_port && self->control_port) {
@@ -448,19 +630,22 @@ void run(LV2_Handle instance, uint32_t n_samples)
         self->latched_valid = true;
         self->latched_loading = self->loading;
     }
+    // From here on an unchanged control row means an unchanged period (what run_block tests).  The row itself can only
+    // stand in for the ports when they ARE one row.
+    set_fast_ok(self, self->ctl_row != nullptr && self->in != nullptr && self->out_1 != nullptr);
 
     if (n_samples == 0) return; // pre-run (:606-609)
     if (!self->in || !self->out_1) return;
 
     bool deferred = false;
-    if (g_hub.batching.load(std::memory_order_acquire) && self->stream >= 0 && (size_t)self->stream < g_hub.slots.size()) {
-        g_hub.slots[self->stream] = EngineHub::Slot{self->in, self->out_1, n_samples, g_hub.epoch};
-        deferred = true;
-        EngineHub::Block& bl = g_hub.blocks[self->stream / EngineHub::kBlockStreams];
-        if (bl.parked.fetch_add(1, std::memory_order_acq_rel) + 1 == bl.live.load(std::memory_order_relaxed)) {
-            const int c = self->stream / g_hub.chunk_streams;
-            EngineHub::Chunk& ch = g_hub.chunks[c];
-            if (ch.blocks_done.fetch_add(1, std::memory_order_acq_rel) + 1 == ch.blocks_live.load(std::memory_order_relaxed)) submit_chunk(c);
+    if (g_hub.batching.load(std::memory_order_acquire)) {
+        // the first instance of a period fixes its n_samples; an instance run with another length renders on its own
+        uint32_t pn = g_hub.period_n.load(std::memory_order_relaxed);
+        if (pn == 0 && g_hub.period_n.compare_exchange_strong(pn, n_samples, std::memory_order_relaxed)) pn = n_samples;
+        if (pn == n_samples) {
+            g_hub.st_ran[self->stream] = g_hub.epoch;
+            deferred = true;
+            park_in_block(self->stream / EngineHub::kBlockStreams, 1);
         }
     }
     if (!deferred) {
@@ -478,14 +663,16 @@ void cleanup(LV2_Handle instance)
 {
     Plugin* self = (Plugin*)instance;
     aidax_stream_close(self->engine, self->stream);
-    free_loaded(self->model);
+    free_loaded(self->engine, self->model);
     {
         std::lock_guard<std::mutex> lk(g_hub.mu);
         g_hub.refs--;
+        g_hub.st_flags[self->stream] = 0;
+        g_hub.port_epoch.fetch_add(1, std::memory_order_acq_rel);
         if (g_hub.blocks[self->stream / EngineHub::kBlockStreams].live.fetch_sub(1) == 1)
             g_hub.chunks[self->stream / g_hub.chunk_streams].blocks_live.fetch_sub(1);
     }
-    delete self;
+    self->~Plugin(); // the storage belongs to the hub's pool
 }
 
 // rt-neural-generic.cpp:707-759
@@ -551,8 +738,10 @@ LV2_Worker_Status work(LV2_Handle instance, LV2_Worker_Respond_Function respond,
         if (aidax_model_load_json(self->engine, path, &model_id, &input_size) == AIDAX_OK) {
             lv2_log_note(&self->logger, "Successfully loaded json file: %s\n", path);
             LoadedModel* m = new LoadedModel{model_id, input_size, strdup(path), p1, p2};
-            // "cache input size for later" (:1082): published before the swap, as in the reference
+            // "cache input size for later" (:1082): published before the swap, as in the reference; the next run() writes
+            // it to the ModelInSize port (the latched row no longer matches the port, so run_block takes the long way)
             self->last_input_size = input_size;
+            self->latched[AIDAX_CTRL_MODELINSIZE] = (float)input_size;
             WorkerApplyMessage reply = {kWorkerApply, m};
             respond(handle, sizeof(reply), &reply);
         } else {
@@ -562,7 +751,7 @@ LV2_Worker_Status work(LV2_Handle instance, LV2_Worker_Respond_Function respond,
         return LV2_WORKER_SUCCESS;
     }
     case kWorkerFree:
-        free_loaded(((const WorkerApplyMessage*)data)->model);
+        free_loaded(self->engine, ((const WorkerApplyMessage*)data)->model);
         return LV2_WORKER_SUCCESS;
     case kWorkerApply:
         break; // should not happen
@@ -597,6 +786,7 @@ LV2_Worker_Status work_response(LV2_Handle instance, uint32_t, const void* data)
         lv2_atom_forge_pop(&self->forge, &frame);
     }
     self->loading = false;
+    set_fast_ok(self, false); // the master gain target changes with `loading`: the next run() latches it
     lv2_log_trace(&self->logger, "loading = false\n");
     return LV2_WORKER_SUCCESS;
 }

@@ -1,0 +1,203 @@
+// probes.cu -- measured roofline denominators for the pipes the chain kernels load ("the builder measures
+// it on the box and states which denominator is used").  MEASURED_PEAKS.json holds HBM copy bandwidth and the cuBLAS
+// bf16 rate only; the recurrence kernels are bound by the XU (MUFU) pipe, the FP32/FP64 CUDA-core pipes and -- in the
+// tcgen05 shape -- by small-N kind::tf32 MMAs, so each of those gets a register/shared-memory resident saturating loop:
+//   [0] FP32  FFMA,  TFLOP/s (2 flop per lane-op)
+//   [1] XU    MUFU.EX2, G lane-ops/s
+//   [2] FP64  DFMA,  TFLOP/s (2 flop per lane-op; the biquads issue unfused DMUL/DADD at the same instruction rate)
+//   [3] XU    F2F f32<->f64 conversions, G lane-ops/s (they share the XU pipe with the MUFU ops)
+//   [4..6] tcgen05.mma kind::tf32 M=128, N = 256 / 160 / 64, K = 8 per instruction, operands in shared memory,
+//          accumulators in TMEM, dense TFLOP/s (2*M*N*K per instruction) -- N = 4H of the LSTM-40 and LSTM-16 tiles
+//   [7] SM clock (MHz) the probes ran at, from clock64() against the event timer
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+
+#include "../../include/aidax.h"
+#include "tc_prims.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256) ffma_probe(float* out, int iters)
+{
+    float a[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = 1.0f + 1e-3f * (float)(threadIdx.x + j);
+    const float x = 0.9999f, y = 1e-4f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = fmaf(a[j], x, y);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += a[j];
+    if (s == 123.456f) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) mufu_probe(float* out, int iters)
+{
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = -0.5f - 1e-3f * (float)(threadIdx.x + j);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[j]));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += a[j];
+    if (s == 123.456f) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) dfma_probe(float* out, int iters)
+{
+    double a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 1.0 + 1e-3 * (double)(threadIdx.x + j);
+    const double x = 0.9999, y = 1e-4;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = fma(a[j], x, y);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += a[j];
+    if (s == 123.456) out[0] = (float)s;
+}
+
+__global__ void __launch_bounds__(256) f2f_probe(float* out, int iters)
+{
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 1.0f + 1e-3f * (float)(threadIdx.x + j);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            double d;
+            asm volatile("cvt.f64.f32 %0, %1;" : "=d"(d) : "f"(a[j]));
+            asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(a[j]) : "d"(d));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += a[j];
+    if (s == 123.456f) out[0] = s;
+}
+
+// One CTA per SM: one thread issues `iters` rounds of 4 K-steps of M128 x N x K8 kind::tf32 MMAs, alternating between
+// two TMEM accumulators, and commits once at the end.  Operands are whatever shared memory holds (zero-filled: the
+// tensor pipe's timing does not depend on the data).
+__global__ void __launch_bounds__(128) tf32_probe(float* out, int N, int iters, long long* cycles)
+{
+    using namespace aidax::tc;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    constexpr int KP = 32; // four K-steps of 8
+    float* A = smem;            // 128 x KP
+    float* B = smem + 128 * KP; // N x KP
+    for (int i = threadIdx.x; i < (128 + N) * KP; i += blockDim.x) smem[i] = 0.f;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
+    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    long long t0 = 0;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_tf32(128, N);
+        const uint32_t lbo_a = 128 * 16, lbo_b = (uint32_t)N * 16, sbo = 128;
+        t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            const uint32_t d = tmem + (uint32_t)(i & 1) * 256;
+#pragma unroll
+            for (int ks = 0; ks < KP / 8; ++ks)
+                mma_tf32(d, make_smem_desc(smem_u32(A) + ks * 2 * lbo_a, lbo_a, sbo), make_smem_desc(smem_u32(B) + ks * 2 * lbo_b, lbo_b, sbo), idesc,
+                         (i > 1 || ks > 0) ? 1u : 0u);
+        }
+        mma_commit(smem_u32(&bar));
+    }
+    mbar_wait(smem_u32(&bar), 0);
+    tc_fence_after();
+    if (threadIdx.x == 0 && blockIdx.x == 0 && cycles) *cycles = clock64() - t0;
+    uint32_t v[16];
+    tmem_ld16(tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16), v);
+    tmem_ld_wait16(v);
+    if (__uint_as_float(v[0]) == 123.456f) out[0] = 1.f;
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+
+template <typename F>
+cudaError_t best_of(int millis, double work_per_launch, double* best_out, F launch)
+{
+    cudaEvent_t a, b;
+    cudaError_t err = cudaEventCreate(&a);
+    if (err != cudaSuccess) return err;
+    err = cudaEventCreate(&b);
+    if (err != cudaSuccess) { cudaEventDestroy(a); return err; }
+    launch(); // warm-up
+    err = cudaDeviceSynchronize();
+    double best = 0.0, spent = 0.0;
+    while (err == cudaSuccess && spent < (double)millis) {
+        cudaEventRecord(a);
+        launch();
+        cudaEventRecord(b);
+        err = cudaEventSynchronize(b);
+        float ms = 0.f;
+        if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, a, b);
+        spent += std::max(ms, 0.01f);
+        if (ms > 0.f) best = std::max(best, work_per_launch / (ms * 1e-3));
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *best_out = best;
+    return err;
+}
+
+} // namespace
+
+extern "C" int aidax_measure_pipe_peaks(int device, int millis, double out[8])
+{
+    if (!out) return AIDAX_ERR_ARG;
+    for (int i = 0; i < 8; ++i) out[i] = 0.0;
+    if (cudaSetDevice(device) != cudaSuccess) return AIDAX_ERR_CUDA;
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) return AIDAX_ERR_CUDA;
+    float* d = nullptr;
+    long long* d_cycles = nullptr;
+    if (cudaMalloc((void**)&d, 64) != cudaSuccess || cudaMalloc((void**)&d_cycles, 8) != cudaSuccess) return AIDAX_ERR_CUDA;
+    const int sms = prop.multiProcessorCount, grid = sms * 8;
+    const int each = std::max(10, millis / 7);
+    cudaError_t err = cudaSuccess;
+    double v = 0.0;
+    const int it32 = 8192, itxu = 2048, it64 = 2048;
+    if (err == cudaSuccess) { err = best_of(each, (double)grid * 256 * 16 * 2.0 * it32, &v, [&] { ffma_probe<<<grid, 256>>>(d, it32); }); out[0] = v / 1e12; }
+    if (err == cudaSuccess) { err = best_of(each, (double)grid * 256 * 8 * (double)itxu, &v, [&] { mufu_probe<<<grid, 256>>>(d, itxu); }); out[1] = v / 1e9; }
+    if (err == cudaSuccess) { err = best_of(each, (double)grid * 256 * 8 * 2.0 * it64, &v, [&] { dfma_probe<<<grid, 256>>>(d, it64); }); out[2] = v / 1e12; }
+    if (err == cudaSuccess) { err = best_of(each, (double)grid * 256 * 8 * 2.0 * itxu, &v, [&] { f2f_probe<<<grid, 256>>>(d, itxu); }); out[3] = v / 1e9; }
+    const int Ns[3] = {256, 160, 64};
+    const int iters = 2048;
+    for (int k = 0; k < 3 && err == cudaSuccess; ++k) {
+        const int N = Ns[k];
+        const size_t smem = (size_t)(128 + N) * 32 * sizeof(float);
+        err = cudaFuncSetAttribute(tf32_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) break;
+        const double flop = (double)sms * iters * 4.0 * 2.0 * 128.0 * N * 8.0;
+        err = best_of(each, flop, &v, [&] { tf32_probe<<<sms, 128, smem>>>(d, N, iters, k == 0 ? d_cycles : nullptr); });
+        out[4 + k] = v / 1e12;
+        if (k == 0 && err == cudaSuccess && v > 0.0) {
+            long long cyc = 0;
+            if (cudaMemcpy(&cyc, d_cycles, 8, cudaMemcpyDeviceToHost) == cudaSuccess && cyc > 0) {
+                const double seconds = flop / v; // duration of the best launch
+                out[7] = (double)cyc / seconds / 1e6;
+            }
+        }
+    }
+    cudaFree(d);
+    cudaFree(d_cycles);
+    return err == cudaSuccess ? AIDAX_OK : AIDAX_ERR_CUDA;
+}

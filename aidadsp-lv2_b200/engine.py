@@ -64,6 +64,8 @@ def load_library():
     lib.aidax_model_register.argtypes = [vp, C.POINTER(ModelDesc), fp, fp, fp, fp, C.c_float, ip]
     lib.aidax_model_load_json.argtypes = [vp, C.c_char_p, ip, ip]
     lib.aidax_model_describe.argtypes = [vp, C.c_int, C.POINTER(ModelDesc)]
+    lib.aidax_model_release.argtypes = [vp, C.c_int]
+    lib.aidax_engine_pci_bus_id.argtypes = [vp, C.c_char_p, C.c_int]
     lib.aidax_stream_open.argtypes = [vp, C.c_double, ip]
     lib.aidax_stream_close.argtypes = [vp, C.c_int]
     lib.aidax_stream_activate.argtypes = [vp, C.c_int]
@@ -162,6 +164,16 @@ class Engine:
         self._chk(self.lib.aidax_model_load_json(self.h, os.fsencode(path), C.byref(mid), C.byref(insz)))
         return mid.value, insz.value
 
+    def release_model(self, mid):
+        """Give back an id from load_json / register_model; the weights go when no stream is bound to it any more."""
+        self._chk(self.lib.aidax_model_release(self.h, mid))
+
+    @property
+    def pci_bus_id(self):
+        buf = C.create_string_buffer(64)
+        self._chk(self.lib.aidax_engine_pci_bus_id(self.h, buf, 64))
+        return buf.value.decode()
+
     def describe_model(self, mid):
         d = ModelDesc()
         self._chk(self.lib.aidax_model_describe(self.h, mid, C.byref(d)))
@@ -256,6 +268,19 @@ def measure_fp32_peak(device=0, millis=200):
     if rc != 0:
         raise AidaxError(rc, lib.aidax_last_error().decode())
     return v.value
+
+
+def measure_pipe_peaks(device=0, millis=700):
+    """Measured pipe peaks (csrc/probes.cu): dict with fp32_tflops, mufu_gops, fp64_tflops, f2f_gops,
+    tf32_tflops_n256 / _n160 / _n64 (tcgen05 kind::tf32, M=128) and the SM clock the probes ran at."""
+    lib = load_library()
+    lib.aidax_measure_pipe_peaks.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
+    v = (C.c_double * 8)()
+    rc = lib.aidax_measure_pipe_peaks(device, millis, v)
+    if rc != 0:
+        raise AidaxError(rc, lib.aidax_last_error().decode())
+    keys = ("fp32_tflops", "mufu_gops", "fp64_tflops", "f2f_gops", "tf32_tflops_n256", "tf32_tflops_n160", "tf32_tflops_n64", "sm_mhz")
+    return {k: float(v[i]) for i, k in enumerate(keys)}
 
 
 # ---- host-only helpers (no GPU needed)

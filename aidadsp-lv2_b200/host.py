@@ -49,6 +49,9 @@ def _load():
         L.aidax_host_last_notify_path.restype = C.c_char_p
         L.aidax_host_save_state.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
         L.aidax_host_restore_state.argtypes = [vp, C.c_int, C.c_char_p]
+        L.aidax_host_set_active.argtypes = [vp, C.c_int]
+        L.aidax_host_is_bulk.argtypes = [vp]
+        L.aidax_host_cpus.argtypes = [vp, C.POINTER(C.c_int), C.c_int]
         _lib = L
     return _lib
 
@@ -74,6 +77,23 @@ class BatchHost:
     @property
     def batched(self):
         return bool(self.lib.aidax_host_is_batched(self.h))
+
+    @property
+    def bulk(self):
+        """True if periods go through the plugin's run_block entry (include/aidax_batch.h)."""
+        return bool(self.lib.aidax_host_is_bulk(self.h))
+
+    @property
+    def cpus(self):
+        """cpus the period threads are pinned to ([] = not pinned)."""
+        buf = (C.c_int * 1024)()
+        n = self.lib.aidax_host_cpus(self.h, buf, 1024)
+        return [int(buf[i]) for i in range(min(n, 1024))]
+
+    def set_active(self, n_active):
+        """Only instances [0, n_active) take part in the following periods."""
+        if self.lib.aidax_host_set_active(self.h, int(n_active)):
+            raise ValueError(self.lib.aidax_host_error().decode())
 
     @property
     def launch_count(self):

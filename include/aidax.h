@@ -28,7 +28,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the C ABI is the only thing a library built with -fvisibility=hidden exports */
 #endif
 
-#define AIDAX_ABI_VERSION 1
+#define AIDAX_ABI_VERSION 2
 
 /* status codes (all entry points returning int) */
 enum {
@@ -132,9 +132,19 @@ int aidax_model_register(aidax_engine* e, const aidax_model_desc* desc, const fl
 /* Parse a reference-schema JSON file and register it.  Same acceptance rules as
  * loadModelFromPath (rt-neural-generic.cpp:963-1085): in_shape[-1] <= 3, in_skip <= 1, gains in
  * dB, samplerate from metadata.samplerate|samplerate if numeric else 48000, layers[0].type in
- * {lstm,gru}, hidden in the variant table.  Identical paths are registered once (cache).
+ * {lstm,gru}, hidden in the variant table.  The reference re-parses the file on every load (:963-1013); here a
+ * file is parsed once per (path, modification time, size) while the result is still held or bound, so N instances
+ * loading one capture share one weight block and a capture re-exported to the same path is read again.
+ * Parsing, packing and the weight upload run WITHOUT the engine lock (the LV2 worker thread must not stall run()).
+ * The returned id is HELD by the caller until aidax_model_release.
  * Returns AIDAX_ERR_MODEL on any failure (the reference returns nullptr). */
 int aidax_model_load_json(aidax_engine* e, const char* path, int* model_id_out, int* input_size_out);
+
+/* Give back an id obtained from aidax_model_load_json / aidax_model_register (the reference frees a DynamicModel in
+ * freeModel on the worker thread, rt-neural-generic.cpp:1093-1101).  Streams bound to the model keep it alive; its
+ * device weights are freed when the last hold and the last binding are gone.  Optional: an id never released stays
+ * valid for the life of the engine. */
+int aidax_model_release(aidax_engine* e, int model_id);
 
 int aidax_model_describe(aidax_engine* e, int model_id, aidax_model_desc* out);
 
@@ -226,9 +236,21 @@ void aidax_host_free(void* p);
  * FFMA) of `device`, measured with a register-resident FFMA loop over all SMs for about `millis` ms. */
 int aidax_measure_fp32_peak(int device, int millis, double* tflops_out);
 
+/* Measured denominators for every pipe the chain kernels load (csrc/probes.cu), each from a register/shared-memory
+ * resident saturating loop run for about millis/7 ms:
+ *   out[0] FP32 FFMA TFLOP/s   out[1] XU MUFU.EX2 G lane-ops/s   out[2] FP64 DFMA TFLOP/s
+ *   out[3] XU F2F (f32<->f64 conversion) G lane-ops/s
+ *   out[4..6] tcgen05.mma kind::tf32 M=128, N=256 / 160 / 64 (K=8 per instruction, operands in shared memory) dense TFLOP/s
+ *   out[7] SM clock in MHz while the tensor probe ran. */
+int aidax_measure_pipe_peaks(int device, int millis, double out[8]);
+
 /* Ceiling of the host-fed path (aidax_render_host): pinned-memory copy rates of `device` over a `bytes`-sized
  * buffer, GB/s: [0] host->device alone, [1] device->host alone, [2] per direction with both running at once. */
 int aidax_measure_pcie(int device, size_t bytes, double gbs_out[3]);
+
+/* PCI bus id of the engine's GPU ("0000:1b:00.0", cudaDeviceGetPCIBusId): lets a host place its threads and pinned
+ * arenas on the GPU's NUMA node (/sys/bus/pci/devices/<id>/local_cpulist). */
+int aidax_engine_pci_bus_id(aidax_engine* e, char* out, int cap);
 
 /* Number of kernel launches issued by the engine since creation (for bench accounting). */
 uint64_t aidax_engine_launch_count(aidax_engine* e);

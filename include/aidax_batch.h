@@ -51,9 +51,29 @@ typedef struct AidaxBatchInterface {
     uint64_t (*launch_count)(void);
     /* Text of the last engine error on this thread. */
     const char* (*last_error)(void);
+
+    /* ---- since AIDAX_BATCH_ABI_VERSION 2 (a host checks abi_version >= 2 before using them) ---- */
+
+    /* Bulk form of run(): has exactly the effect of
+     *     for (i = 0; i < count; ++i) descriptor->run(handles[i], n_samples);
+     * (rt-neural-generic.cpp:484-660) but costs a few nanoseconds per instance on an ordinary period.  An instance
+     * whose control ports hold the values latched by its last run(), whose CONTROL atom port carries no event and
+     * whose model is not being swapped needs no control-rate work at all (the reference would decode the same dB
+     * values into the same gains, find every EQ parameter unchanged and write the same ModelInSize); for those the
+     * plugin only notes that the instance takes part in the period.  Every other instance goes through run() itself.
+     * Differences a host must know about: on the short path the NOTIFY port is not touched (it still holds what the
+     * instance's last run() left there -- an empty sequence unless a model-change notification was written), so the
+     * host must not reset it to a "capacity" chunk beforehand; call run() for an instance whose notification it has
+     * just consumed.  May be called from several threads at once on disjoint sets of instances, between begin() and
+     * end().  Outside a batch it simply loops over run().  Returns 0. */
+    int (*run_block)(void* const* handles, uint32_t count, uint32_t n_samples);
+
+    /* PCI bus id ("0000:1b:00.0") of the engine's GPU, so that a host can pin its threads and arenas to the GPU's NUMA
+     * node (/sys/bus/pci/devices/<id>/local_cpulist).  Returns 0 and fills `out`, or nonzero if there is no engine. */
+    int (*device_pci_bus_id)(char* out, int cap);
 } AidaxBatchInterface;
 
-#define AIDAX_BATCH_ABI_VERSION 1
+#define AIDAX_BATCH_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

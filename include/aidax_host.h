@@ -55,8 +55,22 @@ int aidax_host_load_model(aidax_host* h, int instance, const char* json_path);
 int aidax_host_activate(aidax_host* h);
 int aidax_host_deactivate(aidax_host* h);
 
-/* One audio period: run(n_samples) on every instance, then the worker round trip. */
+/* One audio period: run(n_samples) on every active instance, then the worker round trip.  With a plugin that offers
+ * AidaxBatchInterface::run_block (include/aidax_batch.h) instances with nothing pending are handed over in runs. */
 int aidax_host_run(aidax_host* h, int n_samples);
+
+/* Only instances [0, n_active) take part in the following periods (all instances after open()).  An LV2 host is free
+ * not to run an instance; the bench uses this to find the largest instance count whose period meets the deadline. */
+int aidax_host_set_active(aidax_host* h, int n_active);
+
+/* 1 if periods go through the plugin's bulk entry (run_block), 0 if every instance is run() one by one
+ * (plugins without the extension, AIDAX_HOST_NO_BULK=1). */
+int aidax_host_is_bulk(const aidax_host* h);
+
+/* The cpus the period threads are pinned to (one per thread; thread 0 is the caller of aidax_host_run): cpus local to
+ * the plugin's GPU when the plugin reports its PCI device, rotated by $LOCAL_RANK, else the allowed cpus in order.
+ * AIDAX_HOST_PIN=0 disables pinning.  Returns the count and fills up to `cap` entries. */
+int aidax_host_cpus(const aidax_host* h, int* out, int cap);
 
 /* Number of patch:Set notifications an instance has emitted on its NOTIFY port, and the last path. */
 int aidax_host_notify_count(const aidax_host* h, int instance);

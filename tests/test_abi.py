@@ -54,7 +54,7 @@ def test_plugin_descriptor_surface(native_libs):
 
 def test_abi_version_and_error_string(native_libs):
     lib = engine.load_library()
-    assert lib.aidax_abi_version() == 1
+    assert lib.aidax_abi_version() == 2
     h = C.c_void_p()
     rc = lib.aidax_engine_create(0, 0, 128, C.byref(h))  # invalid size: argument error before any CUDA call
     assert rc == 1 and b"bad" in lib.aidax_last_error()
