@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -71,6 +72,7 @@ struct Family {       // one kernel family = (cell, hidden); cell 2 = streams wi
     int cell, H;
     std::vector<const KernelVariant*> variants; // FP32 variants, sorted by streams per warp ascending
     const KernelVariant* tc = nullptr;          // tensor-core variant (kind 1), if compiled for this hidden size
+    std::vector<const KernelVariant*> tc2;      // ping-pong tensor-core variants (kind 3), preferred one first
 };
 
 struct LaunchPlan {
@@ -79,6 +81,12 @@ struct LaunchPlan {
     size_t tbl_offset_model = 0; // offsets into the uploaded table buffers (ints)
     size_t tbl_offset_slots = 0;
     int max_param_tiles = 0;
+    std::vector<std::pair<int, int>> runs; // the launch's streams as maximal runs [a, b) of consecutive ids
+};
+
+// hooks around the launches of one range (flush_deferred: per-family input waits and output copies)
+struct LaunchHooks {
+    std::function<int(const LaunchPlan&, cudaStream_t)> before, after;
 };
 
 // the launches that render one stream range [first, first + n): block -> (model, slots) tables on the device
@@ -101,6 +109,7 @@ struct aidax_engine {
     std::mutex mu;
     int tile_mode = 0, math_mode = 0;
     int tc_min_streams = 4096; // auto mode: families at least this large run on the tensor-core variant
+    int tc_gen = 1, tc2_split = -1, tc2_atmem = -1; // which tensor-core kernel generation / shape (see choose_variant)
     int sm_count = 148;
     size_t smem_optin = 0, smem_per_sm = 0;
     uint64_t launches = 0;
@@ -144,14 +153,15 @@ struct aidax_engine {
     std::vector<const void*> attr_done;
     // pipelined host rendering: copy-in / copy-out streams, a few kernel streams (so that the kernels of
     // small ranges share the GPU) and per-range events; `pending` = ranges submitted since the last wait
-    static constexpr int kMaxKernelStreams = 8;
+    static constexpr int kMaxKernelStreams = 16;
     cudaStream_t stream_in = nullptr, stream_out = nullptr;
     cudaStream_t kstream[kMaxKernelStreams] = {};
-    int n_kstreams = 4;
+    int n_kstreams = 16; // a heterogeneous period has up to 14 kernel families of a few thousand streams each: all of them fit the GPU at once
     cudaEvent_t ev_fork = nullptr;
     cudaEvent_t ev_fan_fork = nullptr, ev_fan_join[kMaxKernelStreams] = {}; // family fan-out inside one range (launch_all)
     int fan_next = 0;
-    std::vector<cudaEvent_t> ev_in, ev_done, ev_out;
+    std::vector<cudaEvent_t> ev_in, ev_done, ev_out, ev_fam;
+    bool pipeline_families = true; // AIDAX_PIPELINE_FAMILIES=0: deferred ranges wait for every copy-in and copy out after every kernel
     bool defer_hetero = true; // AIDAX_DEFER_HETERO=0: render heterogeneous hand-over ranges one by one (submit_range)
     bool debug_sync = false; // AIDAX_DEBUG_SYNC=1: synchronise after every kernel launch and report which one faulted
     bool trace = false;      // AIDAX_TRACE=1: per-range timeline of the host-fed pipeline on stderr
@@ -196,6 +206,7 @@ static void collect_families(aidax_engine* e)
                 if (f.cell == kv->cell && (kv->cell == 2 || f.H == kv->H)) fam = &f;
             if (!fam) { e->families.push_back(Family{kv->cell, kv->H, {}}); fam = &e->families.back(); }
             if (kv->kind == 1) fam->tc = kv;
+            else if (kv->kind == 3) fam->tc2.push_back(kv);
             else fam->variants.push_back(kv);
         }
     for (Family& f : e->families)
@@ -252,6 +263,12 @@ static cudaError_t upload_rows(aidax_engine* e, cudaStream_t st, T* dev, const T
 
 static cudaError_t sync_kernel_streams(aidax_engine* e);
 
+#ifdef AIDAX_LEGACY_UPLOADS
+constexpr bool kTableZeroFill = true;  // round 1: cudaMalloc + cudaMemset (a fill KERNEL on the legacy stream) + pageable cudaMemcpy
+#else
+constexpr bool kTableZeroFill = false;
+#endif
+
 // Host -> device copy that has LANDED when the call returns, whatever stream consumes the data afterwards.
 // (AIDAX_LEGACY_UPLOADS restores the round-1 behaviour for the fault-reproduction build only, tools/race_probe.sh.)
 static cudaError_t upload_blocking(aidax_engine* e, void* dst, const void* src, size_t bytes)
@@ -278,7 +295,7 @@ static int upload_dirty(aidax_engine* e, int first, int n, cudaStream_t st)
         if (e->d_models.n < md.size()) {
             CUDA_TRY(sync_kernel_streams(e)); // launches in flight still read the old table
             e->d_models.release();
-            CUDA_TRY(e->d_models.alloc(std::max<size_t>(md.size() * 2, 64), /*zero=*/false));
+            CUDA_TRY(e->d_models.alloc(std::max<size_t>(md.size() * 2, 64), kTableZeroFill));
         }
         CUDA_TRY(upload_blocking(e, e->d_models.d, md.data(), md.size() * sizeof(ModelDev)));
         e->models_dirty = false;
@@ -329,7 +346,16 @@ static const KernelVariant* choose_variant(const aidax_engine* e, const Family& 
     // per period at 2048 streams, 129 vs 207 us at 4096 -- register-tiled and tensor-core shape alike --, 234 vs 207 us
     // at 8192) ...
     if (e->tile_mode == 0 && !v.empty() && v.front()->kind == 2 && n_streams <= e->sm_count * 40) return v.front();
-    if (fam.tc && (e->tile_mode == 3 || (e->tile_mode == 0 && n_streams >= e->tc_min_streams))) return fam.tc;
+    if ((fam.tc || !fam.tc2.empty()) && (e->tile_mode == 3 || (e->tile_mode == 0 && n_streams >= e->tc_min_streams))) {
+        // generation 2 (two tiles in ping-pong, kernels_tc2.cuh) unless AIDAX_TC_GEN=1; AIDAX_TC2_SPLIT / AIDAX_TC2_ATMEM pick
+        // among the compiled shapes of a hidden size (measurement runs), default = the first one listed in variants.cu
+        if (e->tc_gen == 2 && !fam.tc2.empty()) {
+            for (const KernelVariant* kv : fam.tc2)
+                if ((e->tc2_split < 0 || kv->L == e->tc2_split) && (e->tc2_atmem < 0 || kv->S == e->tc2_atmem)) return kv;
+            return fam.tc2.front();
+        }
+        if (fam.tc) return fam.tc;
+    }
     if (v.size() == 1) return v[0];
     if (e->tile_mode == 1) return v.front();
     if (e->tile_mode == 2) return v.back();
@@ -381,14 +407,22 @@ static int build_plan(aidax_engine* e, int first, int n, RangePlan** out)
         LaunchPlan lp;
         lp.kv = choose_variant(e, fam, total);
         const int CS = lp.kv->ws * lp.kv->NW;
-        std::vector<int> blk_model, blk_slots;
+        std::vector<int> blk_model, blk_slots, all_slots;
         for (auto& kv : by_model) {
             const std::vector<int>& slots = kv.second;
+            all_slots.insert(all_slots.end(), slots.begin(), slots.end());
             if (kv.first >= 0) lp.max_param_tiles = std::max(lp.max_param_tiles, e->models[kv.first].host.desc.input_size - 1);
             for (size_t off = 0; off < slots.size(); off += CS) {
                 blk_model.push_back(std::max(kv.first, 0));
                 for (int j = 0; j < CS; ++j) blk_slots.push_back(off + j < slots.size() ? slots[off + j] : -1);
             }
+        }
+        std::sort(all_slots.begin(), all_slots.end());
+        for (size_t i = 0; i < all_slots.size();) {
+            size_t j = i + 1;
+            while (j < all_slots.size() && all_slots[j] == all_slots[j - 1] + 1) ++j;
+            lp.runs.emplace_back(all_slots[i], all_slots[j - 1] + 1);
+            i = j;
         }
         lp.n_blocks = (int)blk_model.size();
         lp.tbl_offset_model = e->h_tables.size();
@@ -400,7 +434,7 @@ static int build_plan(aidax_engine* e, int first, int n, RangePlan** out)
     if (rp.d_tables.n < e->h_tables.size()) {
         CUDA_TRY(sync_kernel_streams(e));
         rp.d_tables.release();
-        CUDA_TRY(rp.d_tables.alloc(e->h_tables.size() * 2 + 1024, /*zero=*/false));
+        CUDA_TRY(rp.d_tables.alloc(e->h_tables.size() * 2 + 1024, kTableZeroFill));
     }
     if (!e->h_tables.empty()) {
         CUDA_TRY(sync_kernel_streams(e)); // a previous launch may still read the old table
@@ -412,7 +446,8 @@ static int build_plan(aidax_engine* e, int first, int n, RangePlan** out)
     return AIDAX_OK;
 }
 
-static int launch_all(aidax_engine* e, cudaStream_t st, int first, int n, int n_samples, const float* d_in, float* d_out, int layout, size_t stride)
+static int launch_all(aidax_engine* e, cudaStream_t st, int first, int n, int n_samples, const float* d_in, float* d_out, int layout, size_t stride,
+                      const LaunchHooks* hooks = nullptr)
 {
     int rc = upload_dirty(e, first, n, st);
     if (rc) return rc;
@@ -462,8 +497,10 @@ static int launch_all(aidax_engine* e, cudaStream_t st, int first, int n, int n_
         p.models = e->d_models.d;
         p.sa = e->sa();
         void* args[] = {&p};
+        if (hooks && hooks->before) { const int rh = hooks->before(lp, ls); if (rh) return rh; }
         CUDA_TRY(cudaLaunchKernel(fn, dim3(lp.n_blocks), dim3(kv->NW * 32), args, smem, ls));
         e->launches++;
+        if (hooks && hooks->after) { const int rh = hooks->after(lp, ls); if (rh) return rh; }
         if (e->debug_sync) { // AIDAX_DEBUG_SYNC=1: attribute an asynchronous fault to the launch that caused it
             const cudaError_t err = cudaStreamSynchronize(ls);
             if (err != cudaSuccess)
@@ -534,6 +571,9 @@ int aidax_engine_create(int device, int max_streams, int max_block, aidax_engine
     e->smem_optin = prop.sharedMemPerBlockOptin;
     e->smem_per_sm = prop.sharedMemPerMultiprocessor;
     if (const char* v = std::getenv("AIDAX_TC_MIN_STREAMS")) e->tc_min_streams = std::atoi(v);
+    if (const char* v = std::getenv("AIDAX_TC_GEN")) e->tc_gen = std::atoi(v) == 1 ? 1 : 2;
+    if (const char* v = std::getenv("AIDAX_TC2_SPLIT")) e->tc2_split = std::atoi(v);
+    if (const char* v = std::getenv("AIDAX_TC2_ATMEM")) e->tc2_atmem = std::atoi(v);
     if (const char* v = std::getenv("AIDAX_TILE_MODE")) e->tile_mode = std::max(0, std::min(std::atoi(v), 3)); // initial kernel-shape choice (aidax_engine_configure overrides)
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_in, cudaStreamNonBlocking));
@@ -545,6 +585,7 @@ int aidax_engine_create(int device, int max_streams, int max_block, aidax_engine
     e->trace = std::getenv("AIDAX_TRACE") != nullptr;
     e->debug_sync = std::getenv("AIDAX_DEBUG_SYNC") != nullptr;
     if (const char* v = std::getenv("AIDAX_DEFER_HETERO")) e->defer_hetero = std::atoi(v) != 0;
+    if (const char* v = std::getenv("AIDAX_PIPELINE_FAMILIES")) e->pipeline_families = std::atoi(v) != 0;
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, e->trace ? cudaEventDefault : cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fan_fork, cudaEventDisableTiming));
     for (int k = 0; k < e->n_kstreams; ++k) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fan_join[k], cudaEventDisableTiming));
@@ -590,6 +631,7 @@ int aidax_engine_destroy(aidax_engine* e)
     for (cudaEvent_t ev : e->ev_in) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->ev_done) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->ev_out) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->ev_fam) cudaEventDestroy(ev);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_fan_fork) cudaEventDestroy(e->ev_fan_fork);
     for (cudaEvent_t ev : e->ev_fan_join) if (ev) cudaEventDestroy(ev);
@@ -1099,13 +1141,18 @@ static int submit_range(aidax_engine* e, int first_stream, int n_streams, int n_
     return AIDAX_OK;
 }
 
-// Kernels and copy-out of the ranges submit_range deferred: runs of adjacent ranges are rendered as one range each.
+// Kernels and copy-out of the ranges submit_range deferred: runs of adjacent ranges are rendered as one range each, one
+// launch per kernel family.  The families are pipelined against the copies on both sides: a family's kernel waits only
+// for the copy-in of the ranges that hold its streams (the ranges of a period arrive one after another while the host
+// is still handing over later ones), and its streams are copied out as soon as that kernel is done, while the other
+// families are still running -- instead of copy-in of everything -> all kernels -> copy-out of everything.
 static int flush_deferred(aidax_engine* e)
 {
     std::vector<size_t> order;
     for (size_t i = 0; i < e->pending.size(); ++i) if (e->pending[i].deferred) order.push_back(i);
     if (order.empty()) return AIDAX_OK;
     std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return e->pending[a].first < e->pending[b].first; });
+    size_t fam_ev = 0;
     for (size_t a = 0; a < order.size();) {
         size_t b = a + 1;
         const aidax_engine::PendingRange& r0 = e->pending[order[a]];
@@ -1114,18 +1161,59 @@ static int flush_deferred(aidax_engine* e)
             end += e->pending[order[b]].n;
             ++b;
         }
-        for (size_t k = a; k < b; ++k) CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_in[order[k]], 0));
         const size_t doff = (size_t)r0.first * (size_t)e->max_block;
+        const size_t row = (size_t)r0.n_samples;
+        bool per_family = e->pipeline_families;
+        LaunchHooks hooks;
+        hooks.before = [&](const LaunchPlan& lp, cudaStream_t ls) -> int {
+            for (size_t k = a; k < b; ++k) {
+                const aidax_engine::PendingRange& r = e->pending[order[k]];
+                bool touches = !per_family;
+                for (size_t i = 0; i < lp.runs.size() && !touches; ++i) touches = lp.runs[i].first < r.first + r.n && lp.runs[i].second > r.first;
+                if (touches) CUDA_TRY(cudaStreamWaitEvent(ls, e->ev_in[order[k]], 0));
+            }
+            return AIDAX_OK;
+        };
+        hooks.after = [&](const LaunchPlan& lp, cudaStream_t ls) -> int {
+            if (!per_family) return AIDAX_OK;
+            while (e->ev_fam.size() <= fam_ev) {
+                cudaEvent_t ev;
+                CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                e->ev_fam.push_back(ev);
+            }
+            CUDA_TRY(cudaEventRecord(e->ev_fam[fam_ev], ls));
+            CUDA_TRY(cudaStreamWaitEvent(e->stream_out, e->ev_fam[fam_ev], 0));
+            ++fam_ev;
+            for (const auto& run : lp.runs)
+                for (size_t k = a; k < b; ++k) { // a run of streams may cross hand-over ranges: their host rows need not be adjacent
+                    const aidax_engine::PendingRange& r = e->pending[order[k]];
+                    const int lo = std::max(run.first, r.first), hi = std::min(run.second, r.first + r.n);
+                    if (hi <= lo) continue;
+                    CUDA_TRY(cudaMemcpyAsync(r.out + (size_t)(lo - r.first) * row, e->d_io_out.d + (size_t)lo * (size_t)e->max_block, (size_t)(hi - lo) * row * sizeof(float),
+                                             cudaMemcpyDeviceToHost, e->stream_out));
+                }
+            return AIDAX_OK;
+        };
+        {
+            // a period cut into very many stream runs (models interleaved stream by stream) is cheaper to copy out whole
+            RangePlan* rp = nullptr;
+            const int rcp = build_plan(e, r0.first, end - r0.first, &rp);
+            if (rcp) return rcp;
+            size_t n_runs = 0;
+            for (const LaunchPlan& lp : rp->launches) n_runs += lp.runs.size();
+            if (n_runs > 512) per_family = false;
+        }
         const int rc = launch_all(e, e->stream, r0.first, end - r0.first, r0.n_samples, e->d_io_in.d + doff, e->d_io_out.d + doff, r0.layout,
-                                  (size_t)r0.n_samples);
+                                  (size_t)r0.n_samples, &hooks);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(e->ev_done[order[a]], e->stream));
-        CUDA_TRY(cudaStreamWaitEvent(e->stream_out, e->ev_done[order[a]], 0));
+        if (!per_family) CUDA_TRY(cudaStreamWaitEvent(e->stream_out, e->ev_done[order[a]], 0));
         for (size_t k = a; k < b; ++k) {
             const aidax_engine::PendingRange& r = e->pending[order[k]];
             const size_t off = (size_t)r.first * (size_t)e->max_block;
-            CUDA_TRY(cudaMemcpyAsync(r.out, e->d_io_out.d + off, (size_t)r.n * (size_t)r.n_samples * sizeof(float), cudaMemcpyDeviceToHost,
-                                     e->stream_out));
+            if (!per_family)
+                CUDA_TRY(cudaMemcpyAsync(r.out, e->d_io_out.d + off, (size_t)r.n * (size_t)r.n_samples * sizeof(float), cudaMemcpyDeviceToHost,
+                                         e->stream_out));
             if (k != a) CUDA_TRY(cudaEventRecord(e->ev_done[order[k]], e->stream));
             if (e->trace) CUDA_TRY(cudaEventRecord(e->ev_out[order[k]], e->stream_out));
         }

@@ -319,8 +319,9 @@ struct TcCell {
 
     // Gate nonlinearities + cell update of the 4 (TWO: 8) hidden units whose accumulator columns are in raw0 (and raw1),
     // two units per packed instruction.  hn[2c], hn[2c+1] = new h of the units (4(q+c), +1) and (4(q+c)+2, +3).
-    template <bool TWO>
-    __device__ __forceinline__ static void eval_group(const uint32_t (&raw0)[16], const uint32_t (&raw1)[16], int q, float (&cst)[H],
+    // (NC: length of the caller's state array -- all H units here, the units of one thread part in kernels_tc2.cuh)
+    template <bool TWO, int NC>
+    __device__ __forceinline__ static void eval_group(const uint32_t (&raw0)[16], const uint32_t (&raw1)[16], int q, float (&cst)[NC],
                                                       float2 (&hn)[4])
     {
         constexpr float L2E = 1.4426950408889634f;

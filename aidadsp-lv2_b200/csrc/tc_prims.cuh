@@ -51,6 +51,12 @@ __device__ __forceinline__ void bar_sync(uint32_t id, uint32_t nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// producer side of the same barrier: signals arrival and goes on (the PTX producer/consumer pattern: the warps that only
+// need to tell the MMA issuer "my operand rows are written" do not wait for each other)
+__device__ __forceinline__ void bar_arrive(uint32_t id, uint32_t nthreads)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // ---- TMEM allocation (whole warp executes; column count a power of two >= 32)
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols)
@@ -108,6 +114,33 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
         : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same with the A operand in TENSOR MEMORY ("TS" form): A[m][k] (32-bit tf32 elements) sits at lane m, column a_tmem + k
+// (cute::UMMA::tmem_frg for M = 128: datapath = row, one column per 32-bit element); a K step of 8 advances 8 columns.
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}"
+        :
+        : "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// registers -> TMEM: 4 consecutive 32-bit columns of this thread's own lane (lane = 32*(warp%4) + laneid)
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+}
+// this thread's tcgen05.st have completed (then fence::before_thread_sync + a barrier make them visible to the MMA issuer)
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) : : "memory");
+}
+
 // arrive on `bar` when every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint32_t bar_addr)
 {

@@ -4,6 +4,7 @@
 // (register tile of S streams x 4U gate rows per lane, >= 10 FFMA per 128-bit shared load).
 #include "kernels.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_tc2.cuh"
 #include "kernels_w.cuh"
 #include "variants.h"
 
@@ -31,6 +32,16 @@ static int wsf_tc(int ts, int np) { return TcShape<H>::warp_floats(ts, np); }
       &wsf_tc<Hh>, 1, (TcShape<Hh>::fixed_floats(NTt) + 3) & ~3, RES }
 #define BOTH_TC(Hh, NTt, RES) VT(0, Hh, NTt, RES), VT(1, Hh, NTt, RES)
 
+// ping-pong tensor-core variants (kernels_tc2.cuh): two tiles of 128 streams per CTA, SPLIT threads per stream in the
+// recurrence, A operand in shared (ATM 0) or tensor (ATM 1) memory, RES CTAs per SM.  L carries SPLIT, S carries ATM.
+template <int H, int SPLIT, bool ATM>
+static int wsf_tc2(int ts, int np) { return Tc2Shape<H, SPLIT, ATM>::warp_floats(ts, np); }
+#define VT2(CELL, Hh, SPL, ATM, RES)                                                                     \
+    { CELL, Hh, SPL, ATM, 4 * SPL, 64 / SPL,                                                             \
+      { (const void*)&chain_kernel_tc2<CELL, Hh, SPL, (ATM != 0), RES, 0>, (const void*)&chain_kernel_tc2<CELL, Hh, SPL, (ATM != 0), RES, 1> }, \
+      &wsf_tc2<Hh, SPL, (ATM != 0)>, 3, (Tc2Shape<Hh, SPL, (ATM != 0)>::fixed_floats() + 3) & ~3, RES }
+#define BOTH_TC2(Hh, SPL, ATM, RES) VT2(0, Hh, SPL, ATM, RES), VT2(1, Hh, SPL, ATM, RES)
+
 #ifndef AIDAX_TC_NT32
 #define AIDAX_TC_NT32 3
 #endif
@@ -48,6 +59,30 @@ static int wsf_w(int ts, int np) { return WShape::warp_floats(ts, np); }
       &wsf_w, 2, 0, 2 }
 #define BOTH_W(Hh, NWw) VW(0, Hh, NWw), VW(1, Hh, NWw)
 
+// ping-pong shapes compiled per hidden size: (H, SPLIT, A in TMEM, CTAs per SM); the first is the engine's default.
+// tools/variant.sh overrides a list with -DAIDAX_TC2_LIST_<H>="..." to measure other shapes.
+#ifndef AIDAX_TC2_LIST_8
+#define AIDAX_TC2_LIST_8 BOTH_TC2(8, 1, 1, 4), BOTH_TC2(8, 1, 0, 4),
+#endif
+#ifndef AIDAX_TC2_LIST_12
+#define AIDAX_TC2_LIST_12 BOTH_TC2(12, 1, 1, 2), BOTH_TC2(12, 1, 0, 4),
+#endif
+#ifndef AIDAX_TC2_LIST_16
+#define AIDAX_TC2_LIST_16 BOTH_TC2(16, 1, 1, 2), BOTH_TC2(16, 1, 0, 3), BOTH_TC2(16, 2, 1, 2), BOTH_TC2(16, 2, 0, 2),
+#endif
+#ifndef AIDAX_TC2_LIST_20
+#define AIDAX_TC2_LIST_20 BOTH_TC2(20, 1, 1, 2), BOTH_TC2(20, 1, 0, 3),
+#endif
+#ifndef AIDAX_TC2_LIST_24
+#define AIDAX_TC2_LIST_24 BOTH_TC2(24, 2, 1, 1), BOTH_TC2(24, 1, 0, 2),
+#endif
+#ifndef AIDAX_TC2_LIST_32
+#define AIDAX_TC2_LIST_32 BOTH_TC2(32, 2, 1, 1), BOTH_TC2(32, 4, 1, 1),
+#endif
+#ifndef AIDAX_TC2_LIST_40
+#define AIDAX_TC2_LIST_40 BOTH_TC2(40, 2, 1, 1), BOTH_TC2(40, 5, 1, 1), BOTH_TC2(40, 2, 0, 1),
+#endif
+
 #define CAT_(a, b) a##b
 #define CAT(a, b) CAT_(a, b)
 
@@ -55,19 +90,19 @@ const KernelVariant CAT(kVariantsH, AIDAX_VARIANT_H)[] = {
 #if AIDAX_VARIANT_H == 0
     V(2, 8, 8, 8, 4),
 #elif AIDAX_VARIANT_H == 8
-    BOTH_W(8, 4), BOTH(8, 8, 1, 4), BOTH(8, 8, 4, 4), BOTH(8, 8, 8, 4), BOTH_TC(8, 1, 4),
+    BOTH_W(8, 4), BOTH(8, 8, 1, 4), BOTH(8, 8, 4, 4), BOTH(8, 8, 8, 4), BOTH_TC(8, 1, 4), AIDAX_TC2_LIST_8
 #elif AIDAX_VARIANT_H == 12
-    BOTH_W(12, 4), BOTH(12, 4, 1, 4), BOTH(12, 4, 2, 4), BOTH(12, 4, 4, 4), BOTH_TC(12, 1, 4),
+    BOTH_W(12, 4), BOTH(12, 4, 1, 4), BOTH(12, 4, 2, 4), BOTH(12, 4, 4, 4), BOTH_TC(12, 1, 4), AIDAX_TC2_LIST_12
 #elif AIDAX_VARIANT_H == 16
-    BOTH_W(16, 4), BOTH(16, 16, 1, 4), BOTH(16, 16, 4, 4), BOTH(16, 8, 8, 4), BOTH_TC(16, 1, AIDAX_TC_RES16),
+    BOTH_W(16, 4), BOTH(16, 16, 1, 4), BOTH(16, 16, 4, 4), BOTH(16, 8, 8, 4), BOTH_TC(16, 1, AIDAX_TC_RES16), AIDAX_TC2_LIST_16
 #elif AIDAX_VARIANT_H == 20
-    BOTH(20, 4, 1, 4), BOTH(20, 4, 2, 4), BOTH(20, 4, 4, 4), BOTH_TC(20, 1, 3),
+    BOTH(20, 4, 1, 4), BOTH(20, 4, 2, 4), BOTH(20, 4, 4, 4), BOTH_TC(20, 1, 3), AIDAX_TC2_LIST_20
 #elif AIDAX_VARIANT_H == 24
-    BOTH(24, 8, 1, 4), BOTH(24, 8, 4, 4), BOTH(24, 8, 8, 4), BOTH_TC(24, 1, 3),
+    BOTH(24, 8, 1, 4), BOTH(24, 8, 4, 4), BOTH(24, 8, 8, 4), BOTH_TC(24, 1, 3), AIDAX_TC2_LIST_24
 #elif AIDAX_VARIANT_H == 32
-    BOTH(32, 32, 1, 4), BOTH(32, 16, 4, 4), BOTH(32, 8, 4, 4), BOTH_TC(32, AIDAX_TC_NT32, 1),
+    BOTH(32, 32, 1, 4), BOTH(32, 16, 4, 4), BOTH(32, 8, 4, 4), BOTH_TC(32, AIDAX_TC_NT32, 1), AIDAX_TC2_LIST_32
 #elif AIDAX_VARIANT_H == 40
-    BOTH(40, 8, 1, 4), BOTH(40, 8, 2, 4), BOTH(40, 8, 4, 4), BOTH_TC(40, AIDAX_TC_NT40, 1),
+    BOTH(40, 8, 1, 4), BOTH(40, 8, 2, 4), BOTH(40, 8, 4, 4), BOTH_TC(40, AIDAX_TC_NT40, 1), AIDAX_TC2_LIST_40
 #elif AIDAX_VARIANT_H == 64
     BOTH(64, 32, 1, 4), BOTH(64, 32, 4, 4), BOTH(64, 16, 4, 4),
 #elif AIDAX_VARIANT_H == 80
