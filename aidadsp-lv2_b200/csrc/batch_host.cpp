@@ -190,6 +190,7 @@ struct aidax_host {
     float* in = nullptr;
     float* out = nullptr;
     bool arena_from_plugin = false;
+    bool inplace = false;
     float* controls = nullptr;   // [n][kCtlPitch], 64-byte aligned; port p of instance i at i*kCtlPitch + p - kFirstControl
     float* ctl(int i, int port) { return controls + (size_t)i * kCtlPitch + (port - kFirstControl); }
     const float* ctl(int i, int port) const { return controls + (size_t)i * kCtlPitch + (port - kFirstControl); }
@@ -200,6 +201,7 @@ struct aidax_host {
     // must go through run() itself -- a patch:Set is pending on its CONTROL port, or its NOTIFY port holds something
     // other than the empty sequence its last run() left (first period; a notification the host has just consumed)
     bool bulk = false;
+    bool ports_hint = true;      // this host writes control ports only through aidax_host_set_control (which marks the instance), so it can vouch for the others
     std::vector<void*> handles;
     std::vector<uint8_t> slow;
     int n_active = 0;            // instances [0, n_active) take part in a period (aidax_host_set_active)
@@ -322,7 +324,7 @@ void run_instances(aidax_host* h, int lo, int hi, uint32_t n_samples)
             }
             int j = i + 1;
             while (j < hi && !slow[j]) ++j;
-            h->batch->run_block(h->handles.data() + i, (uint32_t)(j - i), n_samples);
+            h->batch->run_block(h->handles.data() + i, (uint32_t)(j - i), n_samples, h->ports_hint ? AIDAX_RUN_PORTS_UNCHANGED : 0u);
             i = j;
         }
         return;
@@ -490,8 +492,10 @@ aidax_host* aidax_host_open(const char* plugin_so, double sample_rate, int n_ins
     }
     if (no_batch) h->batch = nullptr;
     h->bulk = h->batch && h->batch->abi_version >= 2 && h->batch->run_block && getenv("AIDAX_HOST_NO_BULK") == nullptr;
+    h->ports_hint = getenv("AIDAX_HOST_NO_PORTS_HINT") == nullptr; // (=1: let the plugin compare every control row itself)
 
     h->notify_cap = n_instances <= 8192 ? 2048u : 384u;
+    if (const char* v = getenv("AIDAX_HOST_NOTIFY_CAP")) h->notify_cap = (uint32_t)std::max(16, atoi(v)) & ~7u; // tests: a NOTIFY port too small for a message
     h->inst.resize(n_instances);
     auto instantiate_one = [&](int i) -> bool {
         Instance& in = h->inst[i];
@@ -532,6 +536,11 @@ aidax_host* aidax_host_open(const char* plugin_so, double sample_rate, int n_ins
     }
     memset(h->in, 0, arena_bytes);
     memset(h->out, 0, arena_bytes);
+    if (getenv("AIDAX_HOST_INPLACE")) { // tests: OUT connected to the IN buffer (rt-neural-generic.cpp:613 allows in == out_1)
+        if (h->arena_from_plugin) h->batch->arena_free(h->out); else free(h->out);
+        h->out = h->in;
+        h->inplace = true;
+    }
 
     // ttl defaults (ttl/rt-neural-generic.ttl:92-313)
     if (posix_memalign((void**)&h->controls, 64, (size_t)n_instances * kCtlPitch * sizeof(float)) != 0) { set_err("control arena allocation failed"); return nullptr; }
@@ -572,8 +581,8 @@ void aidax_host_close(aidax_host* h)
             drain_worker(h, in);
             h->desc->cleanup(in.handle);
         }
-    if (h->arena_from_plugin) { h->batch->arena_free(h->in); h->batch->arena_free(h->out); }
-    else { free(h->in); free(h->out); }
+    if (h->arena_from_plugin) { h->batch->arena_free(h->in); if (!h->inplace) h->batch->arena_free(h->out); }
+    else { free(h->in); if (!h->inplace) free(h->out); }
     free(h->controls);
     // the plugin binary stays loaded: it may own process-wide state (CUDA context, engine)
     if (!h->cpus.empty() && g_have_initial_affinity) sched_setaffinity(0, sizeof(g_initial_affinity), &g_initial_affinity);
@@ -595,8 +604,9 @@ size_t aidax_host_stride(const aidax_host* h) { return h ? h->stride : 0; }
 int aidax_host_set_control(aidax_host* h, int instance, int port, float value)
 {
     if (!h || port < 4 || port >= kPortCount || instance >= h->n) { set_err("bad control address"); return 1; }
-    if (instance >= 0) *h->ctl(instance, port) = value;
-    else for (int i = 0; i < h->n; ++i) *h->ctl(i, port) = value;
+    // the instance reads its ports through run() in the next period (see run_instances)
+    if (instance >= 0) { *h->ctl(instance, port) = value; h->slow[instance] = 1; }
+    else for (int i = 0; i < h->n; ++i) { *h->ctl(i, port) = value; h->slow[i] = 1; }
     return 0;
 }
 

@@ -406,7 +406,7 @@ static int build_plan(aidax_engine* e, int first, int n, RangePlan** out)
         if (!total) continue;
         LaunchPlan lp;
         lp.kv = choose_variant(e, fam, total);
-        const int CS = lp.kv->ws * lp.kv->NW;
+        const int CS = lp.kv->cs ? lp.kv->cs : lp.kv->ws * lp.kv->NW;
         std::vector<int> blk_model, blk_slots, all_slots;
         for (auto& kv : by_model) {
             const std::vector<int>& slots = kv.second;

@@ -28,14 +28,16 @@
 
 namespace aidax {
 
-template <int H, int SPLIT, bool ATMEM>
+template <int H, int SPLIT, bool ATMEM, bool PP = true>
 struct Tc2Shape {
     using S = TcShape<H>;
     static constexpr int N = S::N, KP = S::KP, KSTEPS = S::KSTEPS, XP = S::XP;
     static constexpr int UH = H / SPLIT;       // hidden units per thread
     static constexpr int NCH = UH / 4;         // 16-column accumulator chunks per thread
-    static constexpr int NTH = 128 * SPLIT;
-    static constexpr int NW = 4 * SPLIT;
+    static constexpr int TPT = PP ? 2 : 1;     // tiles per thread: both tiles in ping-pong, or one tile per thread group
+    static constexpr int GROUP = 128 * SPLIT;  // threads that own one tile's rows (and meet at its named barrier)
+    static constexpr int NTH = PP ? GROUP : 2 * GROUP;
+    static constexpr int NW = NTH / 32;
     static constexpr int CS = 256;             // streams per CTA: two tiles of 128
     static constexpr int YB = SPLIT > 1 ? SPLIT : 0; // partial Dense sums kept per half until the post-network stage
     static constexpr int TILE_COLS = N + (ATMEM ? 2 * KP : 0); // TMEM columns of one tile: accumulator [| A hi | A lo]
@@ -55,7 +57,8 @@ struct Tc2Shape {
                2 * CS /* slot table, per-stream flags */;
     }
     // audio tiles of the CTA's 8 warp-tiles (32 streams each), expressed per launch warp as the engine sizes it
-    __host__ __device__ static constexpr int warp_floats(int ts, int n_param_tiles) { return (8 / NW) * ts * XP * (1 + n_param_tiles + YB); }
+    // (rounded up: with more than 8 warps a launch warp's share is a fraction of a tile)
+    __host__ __device__ static constexpr int warp_floats(int ts, int n_param_tiles) { return (8 * ts * XP * (1 + n_param_tiles + YB) + NW - 1) / NW; }
 };
 
 struct Tc2Tile {
@@ -76,12 +79,12 @@ struct Tc2Tile {
 
 enum : int { SF_VALID = 1, SF_NET = 2, SF_PREWARM = 4 }; // per-stream flags the filter-stage owner leaves for the recurrence threads
 
-template <int CELL, int H, int SPLIT, bool ATMEM, int MATH>
+template <int CELL, int H, int SPLIT, bool ATMEM, bool PP, int MATH>
 struct Tc2Cell {
-    using Sh = Tc2Shape<H, SPLIT, ATMEM>;
+    using Sh = Tc2Shape<H, SPLIT, ATMEM, PP>;
     using S = TcShape<H>;
     using Base = TcCell<CELL, H, MATH>;
-    static constexpr int UH = Sh::UH, NCH = Sh::NCH, XP = Sh::XP;
+    static constexpr int UH = Sh::UH, NCH = Sh::NCH, XP = Sh::XP, TPT = Sh::TPT;
 
     // 3xTF32 split of four values of this thread's A row (tc::split_tf32 + lo rounded to nearest, as TcCell::store_chunk)
     __device__ __forceinline__ static void store_chunk(const Tc2Tile& tt, int chunk, float2 v01, float2 v23)
@@ -214,31 +217,34 @@ struct Tc2Cell {
     {
 #if !(AIDAX_WHATIF & 1)
         if (issuer) {
-            tc::bar_sync(tt.bar_id, Sh::NTH);   // every thread of the CTA has written its rows of this tile
+            tc::bar_sync(tt.bar_id, Sh::GROUP); // every thread that owns rows of this tile has written them
             if (tc::elect_one()) {
                 tc::tc_fence_after();
                 issue_mmas(tt, b_hi, b_lo);
             }
             __syncwarp();
         } else {
-            tc::bar_arrive(tt.bar_id, Sh::NTH);
+            tc::bar_arrive(tt.bar_id, Sh::GROUP);
         }
 #endif
     }
 
-    // n steps of the cell for this thread's units of row r in both tiles.  Every thread of the CTA must call this with
-    // the same n.  hs: which part of the hidden units (0 .. SPLIT-1); the hs == 0 thread also feeds the input columns.
-    __device__ static void run(Tc2Tile (&tt)[2], float (&cst)[2][UH], const Lane (&ln)[2], const float* dw, int n, float in_gain, float out_gain, bool in_skip,
+    // n steps of the cell for this thread's units of row r in its TPT tiles (both tiles of the CTA in ping-pong, or the one
+    // tile of its thread group).  Every thread of the CTA must call this with the same n.  hs: which part of the hidden
+    // units (0 .. SPLIT-1); the hs == 0 thread also feeds the input columns.
+    __device__ __forceinline__ static void run(Tc2Tile (&tt)[TPT], float (&cst)[TPT][UH], const Lane (&ln)[TPT], const float* dw, int n, float in_gain, float out_gain, bool in_skip,
                                int hs, bool issuer, tc_desc_t b_hi, tc_desc_t b_lo)
     {
         const int u0 = hs * UH, c0 = u0 / 4;
         const float db = hs == 0 ? dw[H] : 0.f;
-        float xg[2] = {0.f, 0.f};
+        float xg[TPT];
+#pragma unroll
+        for (int g = 0; g < TPT; ++g) xg[g] = 0.f;
         if (n <= 0) return;
 
-        // ---- prologue: input columns of step 0, first MMAs of both tiles
+        // ---- prologue: input columns of step 0, first MMAs
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
+        for (int g = 0; g < TPT; ++g) {
             if (hs == 0) {
                 xg[g] = ln[g].xcol ? ln[g].xcol[0] * in_gain : 0.f;
                 const float v1 = ln[g].p1col ? ln[g].p1col[0] : ln[g].p1c;
@@ -251,7 +257,7 @@ struct Tc2Cell {
 
         for (int t = 0; t < n; ++t) {
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
+            for (int g = 0; g < TPT; ++g) {
 #if !(AIDAX_WHATIF & 1)
                 tc::mbar_wait(tt[g].bar_addr, tt[g].phase);
                 tt[g].phase ^= 1u;
@@ -311,24 +317,30 @@ struct Tc2Cell {
 };
 
 // ------------------------------------------------------------------------------------------
-// the fused chain kernel on the ping-pong tensor-core recurrence.  CELL: 0 LSTM, 1 GRU
+// the fused chain kernel on the two-tile tensor-core recurrence.  CELL: 0 LSTM, 1 GRU
+//   PP = true : every thread owns row r of BOTH tiles and alternates their epilogues (128 SPLIT threads)
+//   PP = false: thread group g owns tile g (2 x 128 SPLIT threads); the tiles overlap through the warp scheduler, as in
+//               kernels_tc.cuh, but a row's hidden units are spread over SPLIT warps of the same lane quadrant
 // ------------------------------------------------------------------------------------------
-template <int CELL, int H, int SPLIT, bool ATMEM, int RES, int MATH>
-__global__ void __launch_bounds__(128 * SPLIT, RES) chain_kernel_tc2(const __grid_constant__ RenderParams p)
+template <int CELL, int H, int SPLIT, bool ATMEM, bool PP, int RES, int MATH>
+__global__ void __launch_bounds__(Tc2Shape<H, SPLIT, ATMEM, PP>::NTH, RES) chain_kernel_tc2(const __grid_constant__ RenderParams p)
 {
-    using Sh = Tc2Shape<H, SPLIT, ATMEM>;
+    using Sh = Tc2Shape<H, SPLIT, ATMEM, PP>;
     using S = TcShape<H>;
-    using Cell = Tc2Cell<CELL, H, SPLIT, ATMEM, MATH>;
+    using Cell = Tc2Cell<CELL, H, SPLIT, ATMEM, PP, MATH>;
     using Base = TcCell<CELL, H, MATH>;
-    constexpr int XP = Sh::XP, NTH = Sh::NTH, CS = Sh::CS, UH = Sh::UH;
-    constexpr int FS = SPLIT == 1 ? 2 : 1; // streams per thread in the filter stages (the CTA's 256 streams over its first 256 threads)
+    constexpr int XP = Sh::XP, NTH = Sh::NTH, CS = Sh::CS, UH = Sh::UH, TPT = Sh::TPT;
+    constexpr int FS = NTH >= 256 ? 1 : 2;            // streams per thread in the filter stages: the CTA's 256 streams over its first 256 threads
+    constexpr bool WARP_LOCAL = PP && SPLIT == 1;      // a warp's recurrence reads only audio tiles the same warp staged
     extern __shared__ __align__(128) float smem_tc2[];
     float* smem = smem_tc2;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int q = warp & 3, hs = warp >> 2, row = q * 32 + lane;
-    const bool factive = warp < 8; // filter-stage role: warp w < 8 owns warp-tile w (SPLIT 1: warp w owns w and 4 + w)
+    const int gsel = PP ? 0 : warp / (4 * SPLIT);      // thread group = tile (PP: every thread has both)
+    const int wq = PP ? warp : warp % (4 * SPLIT);
+    const int q = wq & 3, hs = wq >> 2, row = q * 32 + lane;
+    const bool factive = warp < 8; // filter-stage role: warp w < 8 owns warp-tile w (4 warps per CTA: warp w owns w and 4 + w)
     const int blk = blockIdx.x;
     const StreamArrays& sa = p.sa;
 
@@ -386,43 +398,47 @@ __global__ void __launch_bounds__(128 * SPLIT, RES) chain_kernel_tc2(const __gri
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    Tc2Tile tt[2];
+    // ---- this thread's tiles: PP: k = 0, 1 -> tiles 0, 1; otherwise k = 0 -> tile gsel
+    Tc2Tile tt[TPT];
+    int tile_of[TPT];
     tc_desc_t db_hi, db_lo;
     {
         constexpr uint32_t LBO_A = 128 * 16, LBO_B = S::N * 16, SBO = 128;
         db_hi = (tc_desc_t)tc::make_smem_desc(tc::smem_u32(Bh), LBO_B, SBO);
         db_lo = (tc_desc_t)tc::make_smem_desc(tc::smem_u32(Bl), LBO_B, SBO);
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
+        for (int k = 0; k < TPT; ++k) {
+            const int g = PP ? k : gsel;
+            tile_of[k] = g;
             const uint32_t tile_base = tmem_base + g * Sh::TILE_COLS;
             const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-            tt[g].tmem_d = tile_base;
-            tt[g].tmem_ld = tile_base + lane_sel;
-            tt[g].tma_hi = tile_base + S::N;
-            tt[g].tma_lo = tile_base + S::N + S::KP;
-            tt[g].ta_hi = tt[g].tma_hi + lane_sel;
-            tt[g].ta_lo = tt[g].tma_lo + lane_sel;
-            tt[g].a_hi = Abase + g * 2 * S::A_FLOATS + row * 4;
-            tt[g].a_lo = tt[g].a_hi + S::A_FLOATS;
-            tt[g].da_hi = tt[g].da_lo = 0;
+            tt[k].tmem_d = tile_base;
+            tt[k].tmem_ld = tile_base + lane_sel;
+            tt[k].tma_hi = tile_base + S::N;
+            tt[k].tma_lo = tile_base + S::N + S::KP;
+            tt[k].ta_hi = tt[k].tma_hi + lane_sel;
+            tt[k].ta_lo = tt[k].tma_lo + lane_sel;
+            tt[k].a_hi = Abase + g * 2 * S::A_FLOATS + row * 4;
+            tt[k].a_lo = tt[k].a_hi + S::A_FLOATS;
+            tt[k].da_hi = tt[k].da_lo = 0;
             if constexpr (!ATMEM) {
                 const uint32_t a_addr = tc::smem_u32(Abase + g * 2 * S::A_FLOATS);
-                tt[g].da_hi = (tc_desc_t)tc::make_smem_desc(a_addr, LBO_A, SBO);
-                tt[g].da_lo = (tc_desc_t)tc::make_smem_desc(a_addr + S::A_FLOATS * 4, LBO_A, SBO);
+                tt[k].da_hi = (tc_desc_t)tc::make_smem_desc(a_addr, LBO_A, SBO);
+                tt[k].da_lo = (tc_desc_t)tc::make_smem_desc(a_addr + S::A_FLOATS * 4, LBO_A, SBO);
             }
-            tt[g].bar_addr = tc::smem_u32(&bars[g]);
-            tt[g].phase = 0;
-            tt[g].bar_id = 1 + g;
+            tt[k].bar_addr = tc::smem_u32(&bars[g]);
+            tt[k].phase = 0;
+            tt[k].bar_id = 1 + g;
         }
     }
-    const bool issuer = warp == 0;
+    const bool issuer = wq == 0; // the first warp of a tile's thread group issues that tile's MMAs
     if constexpr (ATMEM) {
         // tensor memory is not initialised: the K padding of this thread's A rows must be finite zeros
         if (hs == 0) {
 #pragma unroll
-            for (int g = 0; g < 2; ++g)
+            for (int k = 0; k < TPT; ++k)
 #pragma unroll
-                for (int c = H / 4; c < S::KP / 4; ++c) Cell::store_chunk(tt[g], c, 0.f, 0.f, 0.f, 0.f);
+                for (int c = H / 4; c < S::KP / 4; ++c) Cell::store_chunk(tt[k], c, 0.f, 0.f, 0.f, 0.f);
         }
     }
 
@@ -434,67 +450,66 @@ __global__ void __launch_bounds__(128 * SPLIT, RES) chain_kernel_tc2(const __gri
     auto p2buf_of = [&](int wt) { return n_ptiles >= 2 ? xbuf_of(wt) + 2 * p.ts * XP : nullptr; };
     auto ybuf_of = [&](int wt, int half) { return xbuf_of(wt) + (size_t)(1 + n_ptiles + half) * p.ts * XP; };
 
-    // ---- filter-stage role: FS streams per thread.  SPLIT 1: (tile 0, row), (tile 1, row); SPLIT > 1: (tile warp / 4, row), warps 0..7
+    // ---- filter-stage role: warp w < 8 owns the 32 streams of warp-tile w (with 4 warps: w and 4 + w), one per lane
     int fslot[FS], fwt[FS];
     uint32_t fflags[FS], fdfl[FS];
     bool ffirst[FS];
     bool want_prewarm = false;
 #pragma unroll
     for (int f = 0; f < FS; ++f) {
-        const int g = SPLIT == 1 ? f : (hs & 1);
-        fwt[f] = 4 * g + q;
-        fslot[f] = factive ? wslots[g * 128 + row] : -1;
+        fwt[f] = FS == 2 ? 4 * f + warp : (warp & 7);
+        const int si = fwt[f] * 32 + lane;           // index in the CTA's slot table = tile * 128 + row
+        fslot[f] = factive ? wslots[si] : -1;
         uint32_t cmd = 0;
         if (fslot[f] >= 0) cmd = exec_commands(sa, fslot[f]);
         int sf = fslot[f] >= 0 ? SF_VALID : 0;
         if (cmd & C_SET_MODEL) { sf |= SF_PREWARM; want_prewarm = true; }
-        if (factive) sflags[g * 128 + row] = sf;
+        if (factive) sflags[si] = sf;
     }
     __syncthreads(); // (the slot table and the flags are read across warps below)
-    // ---- recurrence role: units [hs*UH, +UH) of row `row` in both tiles
-    int rslot[2];
+    // ---- recurrence role: units [hs*UH, +UH) of row `row` in this thread's tiles
+    int rslot[TPT];
 #pragma unroll
-    for (int g = 0; g < 2; ++g) rslot[g] = max(wslots[g * 128 + row], 0);
+    for (int k = 0; k < TPT; ++k) rslot[k] = max(wslots[tile_of[k] * 128 + row], 0);
 
     if (__syncthreads_or(want_prewarm)) {
         // loadModelFromPath: reset() then applyModel over 2048 zero samples with the param smoothers parked at the
         // old targets (rt-neural-generic.cpp:1035, 1052-1079)
-        float cst[2][UH];
-        typename Cell::Lane ln[2];
+        float cst[TPT][UH];
+        typename Cell::Lane ln[TPT];
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            Cell::load_state(tt[g], cst[g], sa, rslot[g], false, hs * UH);
-            ln[g].xcol = nullptr; ln[g].p1col = nullptr; ln[g].p2col = nullptr; ln[g].ycol = nullptr;
-            ln[g].p1c = sa.p_mem[rslot[g]];
-            ln[g].p2c = sa.p_mem[(size_t)sa.cap + rslot[g]];
-            ln[g].commit = false;
+        for (int k = 0; k < TPT; ++k) {
+            Cell::load_state(tt[k], cst[k], sa, rslot[k], false, hs * UH);
+            ln[k].xcol = nullptr; ln[k].p1col = nullptr; ln[k].p2col = nullptr; ln[k].ycol = nullptr;
+            ln[k].p1c = sa.p_mem[rslot[k]];
+            ln[k].p2c = sa.p_mem[(size_t)sa.cap + rslot[k]];
+            ln[k].commit = false;
         }
         Cell::run(tt, cst, ln, dw, kPrewarmSteps, md.in_gain, md.out_gain, md.in_skip != 0, hs, issuer, db_hi, db_lo);
 #pragma unroll
-        for (int g = 0; g < 2; ++g)
-            if (sflags[g * 128 + row] & SF_PREWARM) Cell::store_state(tt[g], cst[g], sa, rslot[g], hs * UH);
-        __syncthreads(); // both halves' state is in global memory before anyone reloads it
+        for (int k = 0; k < TPT; ++k)
+            if (sflags[tile_of[k] * 128 + row] & SF_PREWARM) Cell::store_state(tt[k], cst[k], sa, rslot[k], hs * UH);
+        __syncthreads(); // every part's state is in global memory before anyone reloads it
     }
 
     bool any_net_local = false;
 #pragma unroll
     for (int f = 0; f < FS; ++f) {
-        const int g = SPLIT == 1 ? f : (hs & 1);
         fflags[f] = 0; fdfl[f] = 0;
         if (fslot[f] >= 0) { fflags[f] = sa.flags[fslot[f]]; fdfl[f] = sa.dflags[fslot[f]]; }
         ffirst[f] = (fdfl[f] & D_PARAM_FIRST_RUN) != 0;
         const bool net_on = (fflags[f] & F_ENABLED) && (fflags[f] & F_NET);
-        if (net_on) { sflags[g * 128 + row] |= SF_NET; any_net_local = true; }
+        if (net_on) { sflags[fwt[f] * 32 + lane] |= SF_NET; any_net_local = true; }
     }
     const bool any_net = __syncthreads_or(any_net_local) != 0;
 
-    float cst[2][UH]; // recurrent state of this thread's units, in registers across the whole period
-    bool rnet[2];
+    float cst[TPT][UH]; // recurrent state of this thread's units, in registers across the whole period
+    bool rnet[TPT];
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-        const int sf = sflags[g * 128 + row];
-        rnet[g] = (sf & SF_NET) != 0;
-        if (any_net) Cell::load_state(tt[g], cst[g], sa, rslot[g], (sf & SF_VALID) != 0, hs * UH);
+    for (int k = 0; k < TPT; ++k) {
+        const int sf = sflags[tile_of[k] * 128 + row];
+        rnet[k] = (sf & SF_NET) != 0;
+        if (any_net) Cell::load_state(tt[k], cst[k], sa, rslot[k], (sf & SF_VALID) != 0, hs * UH);
     }
 
     for (int t0 = 0; t0 < p.n_samples; t0 += p.ts) {
@@ -550,25 +565,25 @@ __global__ void __launch_bounds__(128 * SPLIT, RES) chain_kernel_tc2(const __gri
                 }
             }
         }
-        if constexpr (SPLIT == 1) __syncwarp(); // a warp reads only the tiles it staged itself
-        else __syncthreads();                   // the other half's warp staged the second tile's columns
+        if constexpr (WARP_LOCAL) __syncwarp();
+        else __syncthreads();                   // other warps staged (part of) the columns this thread's recurrence reads
 
         // ---- the network
         if (any_net) {
-            typename Cell::Lane ln[2];
+            typename Cell::Lane ln[TPT];
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                const int wt = 4 * g + q;
-                ln[g].xcol = xbuf_of(wt) + lane;
-                ln[g].p1col = n_ptiles >= 1 ? p1buf_of(wt) + lane : nullptr;
-                ln[g].p2col = n_ptiles >= 2 ? p2buf_of(wt) + lane : nullptr;
-                ln[g].ycol = SPLIT > 1 ? ybuf_of(wt, hs) + lane : nullptr;
-                ln[g].p1c = 0.f; ln[g].p2c = 0.f;
-                ln[g].commit = rnet[g];
+            for (int k = 0; k < TPT; ++k) {
+                const int wt = 4 * tile_of[k] + q;
+                ln[k].xcol = xbuf_of(wt) + lane;
+                ln[k].p1col = n_ptiles >= 1 ? p1buf_of(wt) + lane : nullptr;
+                ln[k].p2col = n_ptiles >= 2 ? p2buf_of(wt) + lane : nullptr;
+                ln[k].ycol = SPLIT > 1 ? ybuf_of(wt, hs) + lane : nullptr;
+                ln[k].p1c = 0.f; ln[k].p2c = 0.f;
+                ln[k].commit = rnet[k];
             }
             Cell::run(tt, cst, ln, dw, ts, md.in_gain, md.out_gain, md.in_skip != 0, hs, issuer, db_hi, db_lo);
         }
-        if constexpr (SPLIT == 1) __syncwarp();
+        if constexpr (WARP_LOCAL) __syncwarp();
         else __syncthreads();
 
         // ---- stages after the network (:645-655)
@@ -579,7 +594,7 @@ __global__ void __launch_bounds__(128 * SPLIT, RES) chain_kernel_tc2(const __gri
             float* xcol = xbuf_of(wt) + lane;
             if (cslot >= 0 && (flags & F_ENABLED) && !(AIDAX_WHATIF & 8)) {
                 if constexpr (SPLIT > 1) {
-                    // Dense partial sums of the halves + skip + output gain (applyModel, rt-neural-generic.cpp:170-182)
+                    // Dense partial sums of the parts + skip + output gain (applyModel, rt-neural-generic.cpp:170-182)
                     if (any_net && (flags & F_NET)) {
                         const float* y0 = ybuf_of(wt, 0) + lane;
                         const size_t ystep = (size_t)p.ts * XP;
@@ -607,12 +622,13 @@ __global__ void __launch_bounds__(128 * SPLIT, RES) chain_kernel_tc2(const __gri
 #pragma unroll
         for (int f = 0; f < FS; ++f)
             if (factive) store_tile<32, XP>(xbuf_of(fwt[f]), p, wslots + fwt[f] * 32, t0, ts, lane);
-        __syncwarp();
+        if constexpr (WARP_LOCAL) __syncwarp();
+        else __syncthreads();                   // the next sub-block's staging overwrites tiles other warps may still read
     }
 
 #pragma unroll
-    for (int g = 0; g < 2; ++g)
-        if (rnet[g]) Cell::store_state(tt[g], cst[g], sa, rslot[g], hs * UH);
+    for (int k = 0; k < TPT; ++k)
+        if (rnet[k]) Cell::store_state(tt[k], cst[k], sa, rslot[k], hs * UH);
 
     tc::tc_fence_before();
     __syncthreads();

@@ -340,7 +340,7 @@ int batch_device_pci_bus_id(char* out, int cap)
 void run(LV2_Handle instance, uint32_t n_samples);
 
 // AidaxBatchInterface::run_block (include/aidax_batch.h)
-int batch_run_block(void* const* handles, uint32_t count, uint32_t n_samples)
+int batch_run_block(void* const* handles, uint32_t count, uint32_t n_samples, uint32_t call_flags)
 {
     EngineHub& H = g_hub;
     bool bulk = n_samples != 0 && H.batching.load(std::memory_order_acquire);
@@ -365,7 +365,7 @@ int batch_run_block(void* const* handles, uint32_t count, uint32_t n_samples)
         Plugin* p = (Plugin*)handles[i];
         const size_t s = (size_t)(p - H.pool);
         bool fast = s < H.cap && (flags[s] & ST_FAST_OK) != 0;
-        if (fast) {
+        if (fast && !(call_flags & AIDAX_RUN_PORTS_UNCHANGED)) {
             const void* ev = evt[s];
             if (ev != evt_seen) { // idle instances of a batch host share one empty sequence: one look per run of equal pointers
                 evt_seen = ev;

@@ -34,12 +34,15 @@ static int wsf_tc(int ts, int np) { return TcShape<H>::warp_floats(ts, np); }
 
 // ping-pong tensor-core variants (kernels_tc2.cuh): two tiles of 128 streams per CTA, SPLIT threads per stream in the
 // recurrence, A operand in shared (ATM 0) or tensor (ATM 1) memory, RES CTAs per SM.  L carries SPLIT, S carries ATM.
-template <int H, int SPLIT, bool ATM>
-static int wsf_tc2(int ts, int np) { return Tc2Shape<H, SPLIT, ATM>::warp_floats(ts, np); }
+// ATM bit 0: A operand in tensor memory; bit 1: one tile per thread group instead of ping-pong (PP = false).
+template <int H, int SPLIT, bool ATM, bool PP>
+static int wsf_tc2(int ts, int np) { return Tc2Shape<H, SPLIT, ATM, PP>::warp_floats(ts, np); }
+#define TC2_SHAPE(Hh, SPL, ATM) Tc2Shape<Hh, SPL, ((ATM) & 1) != 0, ((ATM) & 2) == 0>
 #define VT2(CELL, Hh, SPL, ATM, RES)                                                                     \
-    { CELL, Hh, SPL, ATM, 4 * SPL, 64 / SPL,                                                             \
-      { (const void*)&chain_kernel_tc2<CELL, Hh, SPL, (ATM != 0), RES, 0>, (const void*)&chain_kernel_tc2<CELL, Hh, SPL, (ATM != 0), RES, 1> }, \
-      &wsf_tc2<Hh, SPL, (ATM != 0)>, 3, (Tc2Shape<Hh, SPL, (ATM != 0)>::fixed_floats() + 3) & ~3, RES }
+    { CELL, Hh, SPL, ATM, TC2_SHAPE(Hh, SPL, ATM)::NW, 256 / TC2_SHAPE(Hh, SPL, ATM)::NW,                \
+      { (const void*)&chain_kernel_tc2<CELL, Hh, SPL, ((ATM) & 1) != 0, ((ATM) & 2) == 0, RES, 0>,       \
+        (const void*)&chain_kernel_tc2<CELL, Hh, SPL, ((ATM) & 1) != 0, ((ATM) & 2) == 0, RES, 1> },     \
+      &wsf_tc2<Hh, SPL, ((ATM) & 1) != 0, ((ATM) & 2) == 0>, 3, (TC2_SHAPE(Hh, SPL, ATM)::fixed_floats() + 3) & ~3, RES, 256 }
 #define BOTH_TC2(Hh, SPL, ATM, RES) VT2(0, Hh, SPL, ATM, RES), VT2(1, Hh, SPL, ATM, RES)
 
 #ifndef AIDAX_TC_NT32
@@ -68,7 +71,7 @@ static int wsf_w(int ts, int np) { return WShape::warp_floats(ts, np); }
 #define AIDAX_TC2_LIST_12 BOTH_TC2(12, 1, 1, 2), BOTH_TC2(12, 1, 0, 4),
 #endif
 #ifndef AIDAX_TC2_LIST_16
-#define AIDAX_TC2_LIST_16 BOTH_TC2(16, 1, 1, 2), BOTH_TC2(16, 1, 0, 3), BOTH_TC2(16, 2, 1, 2), BOTH_TC2(16, 2, 0, 2),
+#define AIDAX_TC2_LIST_16 BOTH_TC2(16, 1, 1, 2), BOTH_TC2(16, 1, 0, 3), BOTH_TC2(16, 2, 1, 2), BOTH_TC2(16, 2, 3, 1),
 #endif
 #ifndef AIDAX_TC2_LIST_20
 #define AIDAX_TC2_LIST_20 BOTH_TC2(20, 1, 1, 2), BOTH_TC2(20, 1, 0, 3),
@@ -77,10 +80,10 @@ static int wsf_w(int ts, int np) { return WShape::warp_floats(ts, np); }
 #define AIDAX_TC2_LIST_24 BOTH_TC2(24, 2, 1, 1), BOTH_TC2(24, 1, 0, 2),
 #endif
 #ifndef AIDAX_TC2_LIST_32
-#define AIDAX_TC2_LIST_32 BOTH_TC2(32, 2, 1, 1), BOTH_TC2(32, 4, 1, 1),
+#define AIDAX_TC2_LIST_32 BOTH_TC2(32, 2, 1, 1), BOTH_TC2(32, 4, 1, 1), BOTH_TC2(32, 2, 3, 1),
 #endif
 #ifndef AIDAX_TC2_LIST_40
-#define AIDAX_TC2_LIST_40 BOTH_TC2(40, 2, 1, 1), BOTH_TC2(40, 5, 1, 1), BOTH_TC2(40, 2, 0, 1),
+#define AIDAX_TC2_LIST_40 BOTH_TC2(40, 2, 1, 1), BOTH_TC2(40, 5, 1, 1), BOTH_TC2(40, 2, 3, 1), BOTH_TC2(40, 2, 2, 1),
 #endif
 
 #define CAT_(a, b) a##b

@@ -15,6 +15,7 @@ struct KernelVariant {
                           // 2 = FP32 warp-per-stream latency shape (kernels_w.cuh)
     int fixed_smem_floats; // shared memory that does not scale with the sub-block length (weights / MMA operands)
     int ctas_per_sm;      // residency the shared-memory budget is sized for
+    int cs;               // streams per CTA if it is not ws * NW (kind 3: always 256), else 0
 };
 
 // defined in variants.cu, compiled once per -DAIDAX_VARIANT_H=<H>

@@ -314,7 +314,8 @@ def e2e_arm(args, wl, paths, n_inst, first_global, n_global, rank, world, local_
             n = nxt
         n_rt = best if best is not None else min(points, key=lambda k: points[k]["us_per_buffer"])
         point(n_rt, args.e2e_steps)   # the reported measurement
-        while not points[n_rt]["meets_deadline"] and n_rt > CHUNK:   # the longer run may sit a hair above the search's
+        # real time means (nearly) every period: the reported count must also keep the 95th percentile inside the deadline
+        while (not points[n_rt]["meets_deadline"] or points[n_rt]["us_p95"] > period_s * 1e6) and n_rt > CHUNK:
             n_rt -= CHUNK
             point(n_rt, args.e2e_steps)
     main = points[n_rt]
@@ -338,7 +339,7 @@ def e2e_arm(args, wl, paths, n_inst, first_global, n_global, rank, world, local_
            "streams_per_gpu": n_rt, "streams_total": n_rt * world, "us_per_buffer": main["us_per_buffer"], "us_p95": main["us_p95"], "us_max": main["us_max"],
            "steps": main["periods"], "realtime_streams": int(n_rt * world) if main["meets_deadline"] else int(main["samples_per_s"] // FS),
            "meets_deadline": main["meets_deadline"], "deadline_us": round(period_s * 1e6, 1), "phase_us": main["phase_us"],
-           "selection": "largest multiple of %d instances per GPU whose mean period stays inside the deadline (search: %s)" %
+           "selection": "largest multiple of %d instances per GPU whose mean AND 95th-percentile period stay inside the deadline (search: %s)" %
                         (CHUNK, ", ".join("%d -> %.0f us" % (k, points[k]["us_per_buffer"]) for k in sorted(points))),
            "path": "aidax-batch-host -> #batch begin() -> run_block() over the instances (control-row scan; run() only for instances with events or changed "
                    "controls) -> each completed chunk of instances is shipped at once (aidax_render_host_submit: pinned H2D -> kernels -> D2H on separate "
@@ -579,13 +580,24 @@ def run_reference_sample(wl, steps, warmup, paths, n_streams=None, seconds=2.5, 
            "us_per_buffer_per_stream_one_core": round(us_stream, 2), "x_realtime_per_core": round(T / FS * 1e6 / us_stream, 1), "host_cpus": cpus}
     avx = os.path.join(ROOT, "oracle", "_ref", "rt-neural-generic-avx2.so")
     if both_flavours and os.path.exists(avx):
+        # In its own process: the two flavours are the same C++ sources built with different vector widths, and their
+        # inline template instantiations (STB_GNU_UNIQUE symbols) would be merged by the dynamic loader if both lived
+        # in one address space -- the second one loaded crashes.
         try:
-            dt2, periods2, _ = _time_reference_binary(avx, wl, paths, n, cores, warmup, steps, seconds, periods_per_step)
+            code = ("import json, sys; sys.path.insert(0, %r); import bench; from aidadsp_lv2_b200 import workloads; "
+                    "wl = workloads.get(%r, %d); "
+                    "dt, periods, _ = bench._time_reference_binary(%r, wl, %r, %d, %d, %d, None, %r); print('AVX2', json.dumps([dt, periods]))"
+                    % (ROOT, wl.name, wl.n_streams, avx, list(paths), n, cores, warmup, seconds))
+            res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+            line = [l for l in res.stdout.splitlines() if l.startswith("AVX2 ")]
+            if res.returncode != 0 or not line:
+                raise RuntimeError("exit %d: %s" % (res.returncode, (res.stderr or "").strip()[-160:]))
+            dt2, periods2 = json.loads(line[-1][5:])
             v2 = n * T * periods2 / dt2
             us2 = dt2 / periods2 / n * cores * 1e6
             out["avx2_fma_flavour"] = {"value": round(v2, 1), "unit": "samples/s", "seconds": round(dt2, 2), "periods": periods2,
                                        "us_per_buffer_per_stream_one_core": round(us2, 2), "x_realtime_per_core": round(T / FS * 1e6 / us2, 1),
-                                       "note": "same sources built with -mavx2 -mfma (RTNEURAL_USE_AVX), not the reference's default"}
+                                       "note": "same sources built with -mavx2 -mfma (RTNEURAL_USE_AVX), not the reference's default; timed in a process of its own"}
         except Exception as ex:
             out["avx2_fma_flavour"] = {"unavailable": str(ex)[:200]}
     return out

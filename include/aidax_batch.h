@@ -65,8 +65,13 @@ typedef struct AidaxBatchInterface {
      * instance's last run() left there -- an empty sequence unless a model-change notification was written), so the
      * host must not reset it to a "capacity" chunk beforehand; call run() for an instance whose notification it has
      * just consumed.  May be called from several threads at once on disjoint sets of instances, between begin() and
-     * end().  Outside a batch it simply loops over run().  Returns 0. */
-    int (*run_block)(void* const* handles, uint32_t count, uint32_t n_samples);
+     * end().  Outside a batch it simply loops over run().  Returns 0.
+     * flags: AIDAX_RUN_PORTS_UNCHANGED = the host asserts that since the last run() / run_block() of each of these
+     * instances it has written none of their control ports and queued no event on their CONTROL ports (a host that
+     * owns the control buffers knows when it writes them).  The plugin then skips the comparison of the 21 control
+     * values per instance as well; an instance that still needs control-rate work for reasons of its own (first period,
+     * a model swap in flight) goes through run() regardless. */
+    int (*run_block)(void* const* handles, uint32_t count, uint32_t n_samples, uint32_t flags);
 
     /* PCI bus id ("0000:1b:00.0") of the engine's GPU, so that a host can pin its threads and arenas to the GPU's NUMA
      * node (/sys/bus/pci/devices/<id>/local_cpulist).  Returns 0 and fills `out`, or nonzero if there is no engine. */
@@ -74,6 +79,7 @@ typedef struct AidaxBatchInterface {
 } AidaxBatchInterface;
 
 #define AIDAX_BATCH_ABI_VERSION 2
+#define AIDAX_RUN_PORTS_UNCHANGED 1u
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -98,19 +98,22 @@ def test_partial_render_ranges_and_reopen(native_libs):
     ref.close()
 
 
-@pytest.mark.parametrize("name,n", [("c3", 8192), ("c4", 65536), ("c5", 262144), ("c2", 378880)])
-def test_full_size_configs(native_libs, name, n):
+@pytest.mark.parametrize("name,n,NB", [("c3", 8192, 32), ("c4", 65536, 375), ("c5", 262144, 375), ("c2", 378880, 16)])
+def test_full_size_configs(native_libs, name, n, NB):
     """BASELINE.json's literal stream counts (and the bench's GPU-filling C2 count) on one GPU, device-resident
     stream-interleaved buffers.  The oracle cannot render that many streams, so parity at full size is:
       (i) a deterministic subset of streams spanning every model and both ends of the batch against the oracle
           (<= 1e-4, north_star tolerance), and
      (ii) the size-independent property: the batch is built from 256 distinct input signals repeated, so two streams
-          with the same model, controls and input must agree bit for bit wherever they sit in the launch."""
+          with the same model, controls and input must agree bit for bit wherever they sit in the launch.
+    C4 and C5 (the configurations BASELINE.json shards over 1/2/4/8 GPUs) run for one second of audio (375 buffers), with
+    the recurrent drift of the subset tracked: the error of the last 0.2 s must not exceed 4x that of the first 0.2 s
+    (or the 2.5e-5 build-to-build floor of the reference itself)."""
     import torch
     wl = workloads.get(name, n)
     eng = ax.Engine(max_streams=n, max_block=T)
     _setup(eng, wl, n)
-    NB, P = 4, 256
+    P = 256
     base = signals.sweep_noise_block(P, T * NB)                      # [P][T*NB]; stream s plays base[s % P]
     n_models = len(wl.models)
     per_model = max(1, 24 // n_models)
@@ -124,6 +127,8 @@ def test_full_size_configs(native_libs, name, n):
     p2 = signals.triangle(1.7, NB, T)
     reps = (n + P - 1) // P
     worst = 0.0
+    per_buf = np.zeros(NB)
+    base_dev = torch.from_numpy(base).cuda()                         # [P][T*NB]
     for b in range(NB):
         c = wl.controls.copy()
         if wl.automate_params:
@@ -131,13 +136,13 @@ def test_full_size_configs(native_libs, name, n):
             ph = (np.arange(n) % P).astype(np.float32) * 0.01
             a1, a2 = np.mod(p1[b] + ph, 1.0).astype(np.float32), np.mod(p2[b] + ph, 1.0).astype(np.float32)
             eng.set_params(0, a1, a2)
-        xb = torch.from_numpy(np.ascontiguousarray(base[:, b * T:(b + 1) * T].T)).cuda().repeat(1, reps)[:, :n].contiguous()  # [T][n]
+        xb = base_dev[:, b * T:(b + 1) * T].t().repeat(1, reps)[:, :n].contiguous()  # [T][n]
         yb = torch.empty_like(xb)
         eng.render_device(xb.data_ptr(), yb.data_ptr(), n, T, layout=ax.LAYOUT_INTERLEAVED)
         eng.synchronize()
         assert bool(torch.isfinite(yb).all())
         # (ii) streams P apart inside one model's run are replicas of each other
-        for m in range(n_models):
+        for m in range(n_models if b % 25 == 0 or b == NB - 1 else 0):
             lo, hi = (m * n + n_models - 1) // n_models, ((m + 1) * n + n_models - 1) // n_models
             k = (hi - lo) // P
             if k >= 2:
@@ -148,7 +153,47 @@ def test_full_size_configs(native_libs, name, n):
             if wl.automate_params:
                 c[ax.CTRL["PARAM1"]], c[ax.CTRL["PARAM2"]] = a1[s], a2[s]
             yo = orcs[s].run(c, base[s % P, b * T:(b + 1) * T])
-            worst = max(worst, float(np.abs(y[:, j] - yo).max()))
+            e = float(np.abs(y[:, j] - yo).max())
+            worst = max(worst, e)
+            per_buf[b] = max(per_buf[b], e)
     assert worst <= 1e-4, worst
+    if NB >= 300:
+        k = NB // 5
+        assert per_buf[-k:].max() <= max(4 * per_buf[:k].max(), 2.5e-5), (per_buf[:k].max(), per_buf[-k:].max())
     assert eng.launch_count >= NB
     eng.close()
+
+
+@pytest.mark.parametrize("name,n,tile_mode", [("c4", 8192, 3), ("c5", 4096, 3), ("c4", 8192, 0)])
+def test_sharding_does_not_change_a_stream(native_libs, name, n, tile_mode):
+    """BASELINE.json configs[3]/[4] are a FIXED total sharded over 1/2/4/8 GPUs (bench.py --scaling strong).  A stream
+    must sound the same whichever shard renders it: the total rendered by one engine against the same streams cut into
+    2 and 4 contiguous shards (sharding.shard_range), each shard its own engine with stream ids starting at 0.  With the
+    kernel shape pinned (tile_mode 3) the result is bit-identical; in auto mode a smaller shard may pick another shape,
+    so the bound is the shape-to-shape tolerance."""
+    from aidadsp_lv2_b200 import sharding
+    wl = workloads.get(name, n)
+    NB = 6
+    x = signals.sweep_noise_block(n, T * NB)
+
+    def render(lo, hi):
+        eng = ax.Engine(max_streams=hi - lo, max_block=T)
+        eng.configure(tile_mode=tile_mode)
+        mids = [eng.register_model(m) for m in wl.models]
+        for s in range(lo, hi):
+            sid = eng.open_stream()
+            eng.set_model(sid, mids[wl.model_of_stream(s, n)])
+            eng.set_controls(sid, wl.controls, loading=False)
+        y = np.concatenate([eng.render_host(np.ascontiguousarray(x[lo:hi, b * T:(b + 1) * T])) for b in range(NB)], axis=1)
+        eng.close()
+        return y
+
+    whole = render(0, n)
+    for world in (2, 4):
+        parts = [render(*sharding.shard_range(n, r, world)) for r in range(world)]
+        y = np.concatenate(parts, axis=0)
+        assert y.shape == whole.shape
+        if tile_mode == 3:
+            assert np.array_equal(y, whole), "world %d: max diff %g" % (world, np.abs(y - whole).max())
+        else:
+            assert np.abs(y - whole).max() <= 2e-5

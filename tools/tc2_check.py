@@ -11,8 +11,9 @@ import numpy as np
 import aidadsp_lv2_b200 as ax
 from aidadsp_lv2_b200 import models
 
-SHAPES = {8: [(1, 1), (1, 0)], 12: [(1, 1), (1, 0)], 16: [(1, 1), (1, 0), (2, 1), (2, 0)], 20: [(1, 1), (1, 0)],
-          24: [(2, 1), (1, 0)], 32: [(2, 1), (4, 1)], 40: [(2, 1), (5, 1), (2, 0)]}
+# (SPLIT, ATM): ATM bit 0 = A operand in tensor memory, bit 1 = one tile per thread group (no ping-pong)
+SHAPES = {8: [(1, 1), (1, 0)], 12: [(1, 1), (1, 0)], 16: [(1, 1), (1, 0), (2, 1), (2, 3)], 20: [(1, 1), (1, 0)],
+          24: [(2, 1), (1, 0)], 32: [(2, 1), (4, 1), (2, 3)], 40: [(2, 1), (5, 1), (2, 3), (2, 2)]}
 
 
 def render(n, hidden, cell, insz, env, tile_mode, math_mode, periods, seed=7):
@@ -43,11 +44,13 @@ def render(n, hidden, cell, insz, env, tile_mode, math_mode, periods, seed=7):
     return np.concatenate(outs, axis=1), launches
 
 
-def check():
+def check(only=None):
     periods = [128, 128, 128, 100, 28, 128]
     bad = 0
     for hidden, shapes in SHAPES.items():
         for cell in (0, 1):
+            if only and (hidden, cell) != only:
+                continue
             insz = 3 if cell == 1 else (2 if hidden in (20, 40) else 1)
             n = 4096 + 130     # ragged: the last CTA has a partly empty second tile
             ref1, _ = render(n, hidden, cell, insz, {"AIDAX_TC_GEN": "1"}, 3, 0, periods)
@@ -82,5 +85,23 @@ def timing(hs):
 
 if __name__ == "__main__":
     if sys.argv[1] == "check":
-        sys.exit(check())
+        if len(sys.argv) > 3:
+            sys.exit(check((int(sys.argv[2]), int(sys.argv[3]))))
+        # one process per (hidden size, cell) with its own time limit: a hang or a fault in one shape must not hide the others
+        import subprocess
+        bad = 0
+        for hidden in SHAPES:
+            for cell in (0, 1):
+                try:
+                    r = subprocess.run([sys.executable, "tools/tc2_check.py", "check", str(hidden), str(cell)], capture_output=True, text=True, timeout=150)
+                    lines = [l for l in r.stdout.splitlines() if l.startswith("H=")]
+                    print("\n".join(lines) if lines else "H=%2d cell=%d: no result, exit %d: %s" % (hidden, cell, r.returncode, (r.stderr or "").strip()[-200:]), flush=True)
+                    bad += 0 if r.returncode == 0 and lines else 1
+                except subprocess.TimeoutExpired as ex:
+                    out = (ex.stdout or b"").decode() if isinstance(ex.stdout, bytes) else (ex.stdout or "")
+                    print("\n".join(l for l in out.splitlines() if l.startswith("H=")), flush=True)
+                    print("H=%2d cell=%d: TIMEOUT (hang) after the lines above" % (hidden, cell), flush=True)
+                    bad += 1
+        print("TC2 CHECK", "FAILED" if bad else "OK", flush=True)
+        sys.exit(bad)
     timing([int(v) for v in sys.argv[2:]] or [16, 40, 32, 24, 20, 12, 8])
