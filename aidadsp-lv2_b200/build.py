@@ -3,7 +3,8 @@ import os
 import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(PKG_DIR, "lib")
+# AIDAX_LIB_DIR: measurement runs point the bindings at a library built with other compile-time choices (tools/variant.sh)
+LIB_DIR = os.environ.get("AIDAX_LIB_DIR") or os.path.join(PKG_DIR, "lib")
 
 
 def lib_path(name):

@@ -109,7 +109,7 @@ struct aidax_engine {
     std::mutex mu;
     int tile_mode = 0, math_mode = 0;
     int tc_min_streams = 4096; // auto mode: families at least this large run on the tensor-core variant
-    int tc_gen = 1, tc2_split = -1, tc2_atmem = -1; // which tensor-core kernel generation / shape (see choose_variant)
+    int tc_gen = 2, tc2_split = -1, tc2_atmem = -1; // which tensor-core kernel generation / shape (see choose_variant)
     int sm_count = 148;
     size_t smem_optin = 0, smem_per_sm = 0;
     uint64_t launches = 0;
@@ -162,10 +162,11 @@ struct aidax_engine {
     int fan_next = 0;
     std::vector<cudaEvent_t> ev_in, ev_done, ev_out, ev_fam;
     bool pipeline_families = true; // AIDAX_PIPELINE_FAMILIES=0: deferred ranges wait for every copy-in and copy out after every kernel
+    int grade_unit = 4096, grade_mid = 16384; // piece sizes of aidax_render_host_submit_graded (AIDAX_GRADE_UNIT / AIDAX_GRADE_MID)
     bool defer_hetero = true; // AIDAX_DEFER_HETERO=0: render heterogeneous hand-over ranges one by one (submit_range)
     bool debug_sync = false; // AIDAX_DEBUG_SYNC=1: synchronise after every kernel launch and report which one faulted
     bool trace = false;      // AIDAX_TRACE=1: per-range timeline of the host-fed pipeline on stderr
-    int trace_left = 3;
+    int trace_left = 3, trace_skip = 0; // AIDAX_TRACE_SKIP=k: leave out the first k multi-range periods (model binding, fade-in)
     struct PendingRange {
         int first, n, n_samples;
         bool deferred;      // kernels not launched yet: the range waits for the period's other heterogeneous ranges (wait_ranges)
@@ -271,17 +272,23 @@ constexpr bool kTableZeroFill = false;
 
 // Host -> device copy that has LANDED when the call returns, whatever stream consumes the data afterwards.
 // (AIDAX_LEGACY_UPLOADS restores the round-1 behaviour for the fault-reproduction build only, tools/race_probe.sh.)
-static cudaError_t upload_blocking(aidax_engine* e, void* dst, const void* src, size_t bytes)
+enum { UP_TABLES = 1, UP_MODELS = 2, UP_WEIGHTS = 4 };
+static cudaError_t upload_blocking(aidax_engine* e, void* dst, const void* src, size_t bytes, int what)
 {
     if (!bytes) return cudaSuccess;
 #ifdef AIDAX_LEGACY_UPLOADS
-    return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    // fault-reproduction build: AIDAX_LEGACY_MASK says which uploads go the round-1 way (default: all of them)
+    static const int mask = std::getenv("AIDAX_LEGACY_MASK") ? std::atoi(std::getenv("AIDAX_LEGACY_MASK")) : 7;
+    if (mask & what) return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
 #else
-    std::lock_guard<std::mutex> lk(e->mu_up);
-    cudaError_t err = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e->stream_up);
-    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream_up);
-    return err;
+    (void)what;
 #endif
+    {
+        std::lock_guard<std::mutex> lk(e->mu_up);
+        cudaError_t err = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e->stream_up);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream_up);
+        return err;
+    }
 }
 
 static int upload_dirty(aidax_engine* e, int first, int n, cudaStream_t st)
@@ -297,7 +304,7 @@ static int upload_dirty(aidax_engine* e, int first, int n, cudaStream_t st)
             e->d_models.release();
             CUDA_TRY(e->d_models.alloc(std::max<size_t>(md.size() * 2, 64), kTableZeroFill));
         }
-        CUDA_TRY(upload_blocking(e, e->d_models.d, md.data(), md.size() * sizeof(ModelDev)));
+        CUDA_TRY(upload_blocking(e, e->d_models.d, md.data(), md.size() * sizeof(ModelDev), UP_MODELS));
         e->models_dirty = false;
     }
     if (!e->any_dirty) return AIDAX_OK;
@@ -347,8 +354,9 @@ static const KernelVariant* choose_variant(const aidax_engine* e, const Family& 
     // at 8192) ...
     if (e->tile_mode == 0 && !v.empty() && v.front()->kind == 2 && n_streams <= e->sm_count * 40) return v.front();
     if ((fam.tc || !fam.tc2.empty()) && (e->tile_mode == 3 || (e->tile_mode == 0 && n_streams >= e->tc_min_streams))) {
-        // generation 2 (two tiles in ping-pong, kernels_tc2.cuh) unless AIDAX_TC_GEN=1; AIDAX_TC2_SPLIT / AIDAX_TC2_ATMEM pick
-        // among the compiled shapes of a hidden size (measurement runs), default = the first one listed in variants.cu
+        // a two-tile shape of kernels_tc2.cuh where one is compiled for this hidden size (variants.cu lists only shapes that
+        // beat the first generation), unless AIDAX_TC_GEN=1; AIDAX_TC2_SPLIT / AIDAX_TC2_ATMEM pick among several compiled
+        // shapes (measurement builds), default = the first one listed
         if (e->tc_gen == 2 && !fam.tc2.empty()) {
             for (const KernelVariant* kv : fam.tc2)
                 if ((e->tc2_split < 0 || kv->L == e->tc2_split) && (e->tc2_atmem < 0 || kv->S == e->tc2_atmem)) return kv;
@@ -431,6 +439,12 @@ static int build_plan(aidax_engine* e, int first, int n, RangePlan** out)
         e->h_tables.insert(e->h_tables.end(), blk_slots.begin(), blk_slots.end());
         rp.launches.push_back(lp);
     }
+    // Launch order: the families with the largest shared-memory / tensor-memory footprint first.  The kernels of a
+    // heterogeneous period run concurrently (launch_all fans them out); an LSTM-40 CTA needs a whole SM's tensor memory, so
+    // launched last it lands on SMs that already hold small-model CTAs and sits in tcgen05.alloc until those retire.
+    std::stable_sort(rp.launches.begin(), rp.launches.end(), [](const LaunchPlan& a, const LaunchPlan& b) {
+        return a.kv->fixed_smem_floats > b.kv->fixed_smem_floats || (a.kv->fixed_smem_floats == b.kv->fixed_smem_floats && a.kv->H > b.kv->H);
+    });
     if (rp.d_tables.n < e->h_tables.size()) {
         CUDA_TRY(sync_kernel_streams(e));
         rp.d_tables.release();
@@ -439,7 +453,7 @@ static int build_plan(aidax_engine* e, int first, int n, RangePlan** out)
     if (!e->h_tables.empty()) {
         CUDA_TRY(sync_kernel_streams(e)); // a previous launch may still read the old table
         // ... and the launch that follows (on a non-blocking kernel stream) must see the new one: see upload_blocking
-        CUDA_TRY(upload_blocking(e, rp.d_tables.d, e->h_tables.data(), e->h_tables.size() * sizeof(int)));
+        CUDA_TRY(upload_blocking(e, rp.d_tables.d, e->h_tables.data(), e->h_tables.size() * sizeof(int), UP_TABLES));
     }
     rp.epoch = e->membership_epoch;
     rp.tile_mode = e->tile_mode;
@@ -583,9 +597,12 @@ int aidax_engine_create(int device, int max_streams, int max_block, aidax_engine
     e->kstream[0] = e->stream;
     for (int k = 1; k < e->n_kstreams; ++k) CUDA_TRY(cudaStreamCreateWithFlags(&e->kstream[k], cudaStreamNonBlocking));
     e->trace = std::getenv("AIDAX_TRACE") != nullptr;
+    if (const char* v = std::getenv("AIDAX_TRACE_SKIP")) e->trace_skip = std::atoi(v);
     e->debug_sync = std::getenv("AIDAX_DEBUG_SYNC") != nullptr;
     if (const char* v = std::getenv("AIDAX_DEFER_HETERO")) e->defer_hetero = std::atoi(v) != 0;
     if (const char* v = std::getenv("AIDAX_PIPELINE_FAMILIES")) e->pipeline_families = std::atoi(v) != 0;
+    if (const char* v = std::getenv("AIDAX_GRADE_UNIT")) e->grade_unit = std::max(128, std::atoi(v));
+    if (const char* v = std::getenv("AIDAX_GRADE_MID")) e->grade_mid = std::max(e->grade_unit, std::atoi(v));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, e->trace ? cudaEventDefault : cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fan_fork, cudaEventDisableTiming));
     for (int k = 0; k < e->n_kstreams; ++k) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fan_join[k], cudaEventDisableTiming));
@@ -664,7 +681,7 @@ static int register_host_model(aidax_engine* e, HostModel&& hm, const std::strin
     ModelEntry me;
     CUDA_TRY(cudaSetDevice(e->device));
     CUDA_TRY(cudaMalloc((void**)&me.d_weights, packed.size() * sizeof(float)));
-    const cudaError_t err = upload_blocking(e, me.d_weights, packed.data(), packed.size() * sizeof(float));
+    const cudaError_t err = upload_blocking(e, me.d_weights, packed.data(), packed.size() * sizeof(float), UP_WEIGHTS);
     if (err != cudaSuccess) {
         cudaFree(me.d_weights);
         return fail(AIDAX_ERR_CUDA, "weight upload failed: %s", cudaGetErrorString(err));
@@ -1230,7 +1247,8 @@ static int wait_ranges(aidax_engine* e)
     // the engine stream is re-joined so that later aidax_render_device calls stay ordered after this period
     cudaError_t err = sync_kernel_streams(e);
     if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream_out);
-    if (e->trace && err == cudaSuccess && e->pending.size() > 1 && e->trace_left > 0) {
+    if (e->trace && err == cudaSuccess && e->pending.size() > 1 && e->trace_skip > 0) --e->trace_skip;
+    else if (e->trace && err == cudaSuccess && e->pending.size() > 1 && e->trace_left > 0) {
         --e->trace_left;
         fprintf(stderr, "aidax trace: %zu ranges (ms after the first submit: copy-in done, kernels done, copy-out done)\n", e->pending.size());
         for (size_t i = 0; i < e->pending.size(); ++i) {
@@ -1291,6 +1309,41 @@ int aidax_render_host_submit(aidax_engine* e, int first_stream, int n_streams, i
     std::lock_guard<std::mutex> lk(e->mu);
     CUDA_TRY(cudaSetDevice(e->device));
     return submit_range(e, first_stream, n_streams, n_samples, in, out, layout, stride);
+}
+
+int aidax_render_host_submit_graded(aidax_engine* e, int first_stream, int n_streams, int n_samples, const float* in, float* out, size_t stride)
+{
+    int rc = render_host_checks(e, first_stream, n_streams, n_samples, in, out, AIDAX_LAYOUT_PLANAR, stride);
+    if (rc) return rc;
+    if (n_samples == 0 || n_streams == 0) return AIDAX_OK;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    // A period that is complete when it is handed over is bound by the copies: its duration is the copy-in of the first
+    // piece (nothing else can run yet) + the remaining copy-in + kernel and copy-out of the LAST piece (nothing overlaps
+    // them).  So the pieces are small at both ends and large in the middle, where a piece only has to keep both copy
+    // engines and the SMs busy: 4096, 8192, 16384 ... 16384, 8192, 4096 streams (4096 = the smallest batch that still takes
+    // the tensor-core shape).
+    const int unit = e->grade_unit, mid = e->grade_mid;
+    int done = 0;
+    std::vector<int> tail;
+    int left = n_streams;
+    std::vector<int> pieces;
+    if (left > 2 * unit) { pieces.push_back(unit); left -= unit; }
+    if (left > 6 * unit) { pieces.push_back(2 * unit); left -= 2 * unit; }
+    if (left > 2 * unit) { tail.push_back(unit); left -= unit; }
+    if (left > 6 * unit) { tail.push_back(2 * unit); left -= 2 * unit; }
+    while (left > 0) {
+        const int take = left >= 2 * mid ? mid : left; // the last middle piece takes the remainder (< 2 mid)
+        pieces.push_back(take);
+        left -= take;
+    }
+    for (size_t i = tail.size(); i-- > 0;) pieces.push_back(tail[i]);
+    for (int take : pieces) {
+        rc = submit_range(e, first_stream + done, take, n_samples, in + (size_t)done * stride, out + (size_t)done * stride, AIDAX_LAYOUT_PLANAR, stride);
+        if (rc) return rc;
+        done += take;
+    }
+    return AIDAX_OK;
 }
 
 int aidax_render_host_wait(aidax_engine* e)

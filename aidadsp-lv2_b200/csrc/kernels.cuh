@@ -212,6 +212,82 @@ __device__ __forceinline__ void pass_dc_master(float* xcol, int ts, const Stream
     if (master_on) sa.master_mem[slot] = mem;
 }
 
+// All filter/gain stages on one side of the network as ONE software-pipelined pass: up to six biquads and the side's
+// gain ramp.  PRE : in_lpf -> [pre-gain ramp] -> depth -> bass -> mid -> treble -> presence   (run(), :622-630)
+//           POST: dc blocker -> depth -> bass -> mid -> treble -> presence -> [master ramp]   (:645-655)
+// `on` bit k: stage k's biquad runs (an EQ that is bypassed, on the other side of the network or in band-pass mode
+// switches its stages off).  In iteration t stage k works on sample t-k, so the six double-precision recurrences
+// (serial chains of three dependent DMUL/DADD per sample, plus the float<->double conversions on the XU pipe) are
+// independent instruction streams; with the stages as separate passes the single-biquad ones (in_lpf + gain,
+// dc + master) ran one dependent chain per thread.  Every filter still sees exactly its own input sequence with the
+// reference's operation order and the float narrowing between stages: bit-identical to the separate passes.
+template <int XP, bool POST>
+__device__ __forceinline__ void pass_fused(float* xcol, int ts, const StreamArrays& sa, int slot, uint32_t on)
+{
+    constexpr int W[6] = {POST ? BQ_DC : BQ_INLPF, BQ_DEPTH, BQ_BASS, BQ_MID, BQ_TREBLE, BQ_PRESENCE};
+    constexpr int GA = POST ? 5 : 0; // the gain ramp multiplies the value that leaves this stage
+    const float coef = sa.exp_coef[slot];
+    const float tgt = __fmul_rn(POST ? sa.master_target[slot] : sa.pre_target[slot], __fsub_rn(1.f, coef));
+    float mem = POST ? sa.master_mem[slot] : sa.pre_mem[slot];
+    BiquadReg f[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        f[k].a0 = f[k].a1 = f[k].a2 = f[k].b1 = f[k].b2 = f[k].z1 = f[k].z2 = 0.0;
+        if ((on >> k) & 1u) f[k].load(sa, W[k], slot);
+    }
+    auto stage = [&](int k, float v) -> float {
+        if ((on >> k) & 1u) v = f[k].process(v);
+        if (k == GA) v = __fmul_rn(v, exp_smooth_next(mem, coef, tgt));
+        return v;
+    };
+    float l[5];
+    if (ts >= 6) {
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {  // fill: stage k <= t takes sample t - k
+#pragma unroll
+            for (int k = 4; k >= 0; --k)
+                if (k <= t) l[k] = stage(k, k == 0 ? xcol[t * XP] : l[k - 1]);
+        }
+#pragma unroll 2
+        for (int t = 5; t < ts; ++t) {
+            const float o = stage(5, l[4]);
+            l[4] = stage(4, l[3]);
+            l[3] = stage(3, l[2]);
+            l[2] = stage(2, l[1]);
+            l[1] = stage(1, l[0]);
+            l[0] = stage(0, xcol[t * XP]);
+            xcol[(t - 5) * XP] = o;
+        }
+#pragma unroll
+        for (int d = 0; d < 5; ++d) {  // drain: stage k > d takes sample ts + d - k
+            xcol[(ts + d - 5) * XP] = stage(5, l[4]);
+#pragma unroll
+            for (int k = 4; k > d; --k) l[k] = stage(k, l[k - 1]);
+        }
+    } else {
+        for (int t = 0; t < ts; ++t) {
+            float v = xcol[t * XP];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) v = stage(k, v);
+            xcol[t * XP] = v;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        if ((on >> k) & 1u) f[k].store(sa, W[k], slot);
+    if (POST) sa.master_mem[slot] = mem;
+    else sa.pre_mem[slot] = mem;
+}
+// which stages of pass_fused run for a stream's flag word
+__device__ __forceinline__ uint32_t fused_stages_pre(uint32_t flags)
+{
+    return ((flags & F_LPF) ? 1u : 0u) | ((flags & F_EQ_PRE) ? ((flags & F_EQ_BANDPASS) ? 1u << 3 : 0x3Eu) : 0u);
+}
+__device__ __forceinline__ uint32_t fused_stages_post(uint32_t flags)
+{
+    return ((flags & F_DC) ? 1u : 0u) | ((flags & F_EQ_POST) ? ((flags & F_EQ_BANDPASS) ? 1u << 3 : 0x3Eu) : 0u);
+}
+
 // LinearValueSmoother for PARAM1/2 (common/ValueSmoother.hpp:209-240) as driven by run()
 // (rt-neural-generic.cpp:633-641) and applyModel (:194, 218-219): target change detection with
 // FLT_EPSILON, step recomputed only on change, first-run snap, one next() per sample.

@@ -55,6 +55,10 @@
 #endif
 // Which exponentials of the gate epilogue are evaluated on the FMA pipe instead of the XU pipe (bit per site, see
 // TcCell::ope2): measured slower for H = 16 (+2 % with the tanh(c') site alone, +30 % with all), so none.
+// 1: all filter/gain stages on one side of the network as ONE six-stage software pipeline (kernels.cuh: pass_fused)
+#ifndef AIDAX_FUSED_PASSES
+#define AIDAX_FUSED_PASSES 0
+#endif
 #ifndef AIDAX_POLY_EX2
 #define AIDAX_POLY_EX2 0
 #endif
@@ -664,8 +668,12 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
         // ---- stages before the network (run(), rt-neural-generic.cpp:622-644)
         if (cslot >= 0 && enabled && !(AIDAX_WHATIF & 8)) {
             float* xcol = xbuf + lane;
+#if AIDAX_FUSED_PASSES
+            pass_fused<XP, false>(xcol, ts, sa, cslot, fused_stages_pre(flags));
+#else
             pass_lpf_pregain<XP>(xcol, ts, sa, cslot, (flags & F_LPF) != 0);
             if (flags & F_EQ_PRE) pass_eq<XP>(xcol, ts, sa, cslot, (flags & F_EQ_BANDPASS) != 0);
+#endif
             if (net_on) {
                 pass_param<XP>(p1buf ? p1buf + lane : nullptr, ts, sa, 0, cslot, first_run, input_size >= 2);
                 pass_param<XP>(p2buf ? p2buf + lane : nullptr, ts, sa, 1, cslot, first_run, input_size >= 3);
@@ -688,6 +696,9 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
         // ---- stages after the network (:645-655)
         if (cslot >= 0 && enabled && !(AIDAX_WHATIF & 8)) {
             float* xcol = xbuf + lane;
+#if AIDAX_FUSED_PASSES
+            pass_fused<XP, true>(xcol, ts, sa, cslot, fused_stages_post(flags));
+#else
             const bool dc_on = (flags & F_DC) != 0;
             if (flags & F_EQ_POST) {
                 if (dc_on) pass_biquad<XP>(xcol, ts, sa, BQ_DC, cslot);
@@ -696,6 +707,7 @@ __global__ void __launch_bounds__(NT * 128, RES) chain_kernel_tc(const __grid_co
             } else {
                 pass_dc_master<XP>(xcol, ts, sa, cslot, dc_on, true);
             }
+#endif
         }
         __syncwarp();
         store_tile<32, XP>(xbuf, p, wslots, t0, ts, lane);

@@ -169,8 +169,10 @@ struct Tc2Cell {
             store_chunk(tt, u0 / 4 + c, hv[0], hv[1], hv[2], hv[3]);
         }
     }
-    // LSTM: h is read back from the A row as hi + (lo as the tensor core sees it), see TcCell::store_state
-    __device__ __forceinline__ static void store_state(const Tc2Tile& tt, const float (&cst)[UH], const StreamArrays& sa, int slot, int u0)
+    // LSTM: h is read back from the A row as hi + (lo as the tensor core sees it), see TcCell::store_state.
+    // `write`: per-lane (streams of one warp differ: network bypassed, not bound yet ...).  The read-back from tensor memory
+    // is a warp-collective tcgen05.ld, so EVERY lane executes it and only the global stores are predicated.
+    __device__ __forceinline__ static void store_state(const Tc2Tile& tt, const float (&cst)[UH], const StreamArrays& sa, int slot, int u0, bool write)
     {
         const size_t cap = (size_t)sa.cap;
 #pragma unroll
@@ -190,6 +192,7 @@ struct Tc2Cell {
                     lv[0] = lo.x; lv[1] = lo.y; lv[2] = lo.z; lv[3] = lo.w;
                 }
             }
+            if (!write) continue;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int u = u0 + 4 * c + i;
@@ -488,7 +491,7 @@ __global__ void __launch_bounds__(Tc2Shape<H, SPLIT, ATMEM, PP>::NTH, RES) chain
         Cell::run(tt, cst, ln, dw, kPrewarmSteps, md.in_gain, md.out_gain, md.in_skip != 0, hs, issuer, db_hi, db_lo);
 #pragma unroll
         for (int k = 0; k < TPT; ++k)
-            if (sflags[tile_of[k] * 128 + row] & SF_PREWARM) Cell::store_state(tt[k], cst[k], sa, rslot[k], hs * UH);
+            Cell::store_state(tt[k], cst[k], sa, rslot[k], hs * UH, (sflags[tile_of[k] * 128 + row] & SF_PREWARM) != 0);
         __syncthreads(); // every part's state is in global memory before anyone reloads it
     }
 
@@ -550,8 +553,12 @@ __global__ void __launch_bounds__(Tc2Shape<H, SPLIT, ATMEM, PP>::NTH, RES) chain
             float* p1b = p1buf_of(wt);
             float* p2b = p2buf_of(wt);
             if (cslot >= 0 && (flags & F_ENABLED) && !(AIDAX_WHATIF & 8)) {
+#if AIDAX_FUSED_PASSES
+                pass_fused<XP, false>(xcol, ts, sa, cslot, fused_stages_pre(flags));
+#else
                 pass_lpf_pregain<XP>(xcol, ts, sa, cslot, (flags & F_LPF) != 0);
                 if (flags & F_EQ_PRE) pass_eq<XP>(xcol, ts, sa, cslot, (flags & F_EQ_BANDPASS) != 0);
+#endif
                 if (flags & F_NET) {
                     pass_param<XP>(p1b ? p1b + lane : nullptr, ts, sa, 0, cslot, ffirst[f], input_size >= 2);
                     pass_param<XP>(p2b ? p2b + lane : nullptr, ts, sa, 1, cslot, ffirst[f], input_size >= 3);
@@ -608,6 +615,9 @@ __global__ void __launch_bounds__(Tc2Shape<H, SPLIT, ATMEM, PP>::NTH, RES) chain
                         }
                     }
                 }
+#if AIDAX_FUSED_PASSES
+                pass_fused<XP, true>(xcol, ts, sa, cslot, fused_stages_post(flags));
+#else
                 const bool dc_on = (flags & F_DC) != 0;
                 if (flags & F_EQ_POST) {
                     if (dc_on) pass_biquad<XP>(xcol, ts, sa, BQ_DC, cslot);
@@ -616,6 +626,7 @@ __global__ void __launch_bounds__(Tc2Shape<H, SPLIT, ATMEM, PP>::NTH, RES) chain
                 } else {
                     pass_dc_master<XP>(xcol, ts, sa, cslot, dc_on, true);
                 }
+#endif
             }
         }
         __syncwarp();
@@ -628,7 +639,7 @@ __global__ void __launch_bounds__(Tc2Shape<H, SPLIT, ATMEM, PP>::NTH, RES) chain
 
 #pragma unroll
     for (int k = 0; k < TPT; ++k)
-        if (rnet[k]) Cell::store_state(tt[k], cst[k], sa, rslot[k], hs * UH);
+        Cell::store_state(tt[k], cst[k], sa, rslot[k], hs * UH, rnet[k]);
 
     tc::tc_fence_before();
     __syncthreads();

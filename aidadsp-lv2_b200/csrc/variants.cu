@@ -62,28 +62,32 @@ static int wsf_w(int ts, int np) { return WShape::warp_floats(ts, np); }
       &wsf_w, 2, 0, 2 }
 #define BOTH_W(Hh, NWw) VW(0, Hh, NWw), VW(1, Hh, NWw)
 
-// ping-pong shapes compiled per hidden size: (H, SPLIT, A in TMEM, CTAs per SM); the first is the engine's default.
-// tools/variant.sh overrides a list with -DAIDAX_TC2_LIST_<H>="..." to measure other shapes.
+// Two-tile shapes (kernels_tc2.cuh) compiled per hidden size: (H, SPLIT, ATM, CTAs per SM); ATM bit 0 = A operand in tensor
+// memory, bit 1 = one tile per thread group (no ping-pong).  Only shapes that BEAT kernels_tc.cuh on B200 are in the
+// default build (profiles/r02c_tc2_time.txt: LSTM-40 3.18 vs 3.31 ms per 262144-stream period with the hidden units of a
+// row split over two warps and A in tensor memory; every ping-pong shape and every other hidden size measured slower); the
+// engine takes a listed shape in preference to the first-generation kernel.  tools/variant.sh overrides a list with
+// -DAIDAX_TC2_LIST_<H>="..." to measure others (tools/tc2_check.py checks and times them).
 #ifndef AIDAX_TC2_LIST_8
-#define AIDAX_TC2_LIST_8 BOTH_TC2(8, 1, 1, 4), BOTH_TC2(8, 1, 0, 4),
+#define AIDAX_TC2_LIST_8
 #endif
 #ifndef AIDAX_TC2_LIST_12
-#define AIDAX_TC2_LIST_12 BOTH_TC2(12, 1, 1, 2), BOTH_TC2(12, 1, 0, 4),
+#define AIDAX_TC2_LIST_12
 #endif
 #ifndef AIDAX_TC2_LIST_16
-#define AIDAX_TC2_LIST_16 BOTH_TC2(16, 1, 1, 2), BOTH_TC2(16, 1, 0, 3), BOTH_TC2(16, 2, 1, 2), BOTH_TC2(16, 2, 3, 1),
+#define AIDAX_TC2_LIST_16
 #endif
 #ifndef AIDAX_TC2_LIST_20
-#define AIDAX_TC2_LIST_20 BOTH_TC2(20, 1, 1, 2), BOTH_TC2(20, 1, 0, 3),
+#define AIDAX_TC2_LIST_20
 #endif
 #ifndef AIDAX_TC2_LIST_24
-#define AIDAX_TC2_LIST_24 BOTH_TC2(24, 2, 1, 1), BOTH_TC2(24, 1, 0, 2),
+#define AIDAX_TC2_LIST_24
 #endif
 #ifndef AIDAX_TC2_LIST_32
-#define AIDAX_TC2_LIST_32 BOTH_TC2(32, 2, 1, 1), BOTH_TC2(32, 4, 1, 1), BOTH_TC2(32, 2, 3, 1),
+#define AIDAX_TC2_LIST_32
 #endif
 #ifndef AIDAX_TC2_LIST_40
-#define AIDAX_TC2_LIST_40 BOTH_TC2(40, 2, 1, 1), BOTH_TC2(40, 5, 1, 1), BOTH_TC2(40, 2, 3, 1), BOTH_TC2(40, 2, 2, 1),
+#define AIDAX_TC2_LIST_40 BOTH_TC2(40, 2, 3, 1),
 #endif
 
 #define CAT_(a, b) a##b

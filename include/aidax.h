@@ -227,6 +227,11 @@ int aidax_engine_synchronize(aidax_engine* e);
 int aidax_render_host_submit(aidax_engine* e, int first_stream, int n_streams, int n_samples,
                              const float* in, float* out, int layout, size_t stride);
 int aidax_render_host_wait(aidax_engine* e);
+/* submit() for a LARGE planar range that is complete at hand-over: the engine cuts it into pieces that are small at both
+ * ends of the period (the first copy-in and the last kernel + copy-out overlap nothing) and large in between, and submits
+ * them in order.  What the #batch extension's end() uses when the whole period arrived through run_block(). */
+int aidax_render_host_submit_graded(aidax_engine* e, int first_stream, int n_streams, int n_samples,
+                                    const float* in, float* out, size_t stride);
 
 /* Pinned host memory for audio arenas (cudaHostAlloc / cudaFreeHost). */
 void* aidax_host_alloc(size_t bytes);

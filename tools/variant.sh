@@ -12,7 +12,8 @@ while [ $# -ge 2 ]; do
       nvcc $NVF -DAIDAX_VARIANT_H=$h $flags -c csrc/variants.cu -o $d/variants_h$h.o || exit 1
       objs="$objs $d/variants_h$h.o"; skip="$skip -e h$h.o"
     done
-    nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $d/libaidax.so build/engine.o $(ls build/variants_h*.o | grep -v $skip) $objs -cudart shared &&
+    nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $d/libaidax.so build/engine.o build/probes.o $(ls build/variants_h*.o | grep -v $skip) $objs -cudart shared &&
+    cp lib/rt-neural-generic.so lib/libaidax_host.so $d/ &&   # the plugin finds libaidax.so next to itself ($ORIGIN): AIDAX_LIB_DIR=$d runs everything on the variant
     rm -f $d/variants_h*.o && echo "built $d ($flags)" ) &
 done
 wait
