@@ -131,6 +131,35 @@ __global__ void __launch_bounds__(128) tf32_probe(float* out, int N, int iters, 
     if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
 }
 
+// K6: the bench's synthetic input, generated where it is consumed.  x[s][n] = 0.5 sin(2 pi (20 t + 999 t^2) +
+// 0.37 s) + 0.05 u(s, n), t = n / 48000 -- the 20 Hz -> 20 kHz sweep over 10 s of SURVEY 8(d) with a per-stream phase --
+// and u a counter-based uniform in [-1, 1) (32-bit integer hash of stream, sample index and seed: the numpy mirror in
+// aidadsp_lv2_b200/signals.py reproduces it bit for bit).  The sweep is evaluated in double precision and rounded once.
+__device__ __forceinline__ uint32_t hash32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__global__ void __launch_bounds__(256) gen_input_kernel(float* out, int first_stream, int n_streams, long long start, int n_samples, int layout, size_t stride,
+                                                        uint32_t seed)
+{
+    const long long total = (long long)n_streams * n_samples;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        // consecutive threads write consecutive addresses in either layout
+        const int s = layout == AIDAX_LAYOUT_PLANAR ? (int)(i / n_samples) : (int)(i % n_streams);
+        const int k = layout == AIDAX_LAYOUT_PLANAR ? (int)(i % n_samples) : (int)(i / n_streams);
+        const long long n = start + k;
+        const uint32_t gs = (uint32_t)(first_stream + s);
+        const uint32_t h = hash32(gs * 0x9E3779B1u + (uint32_t)n * 0x85EBCA77u + seed);
+        const float u = (float)(h >> 8) * 1.1920928955078125e-07f - 1.0f; // 24 bits -> [-1, 1), exact
+        const double t = (double)n / 48000.0;
+        const double phase = 6.283185307179586 * (20.0 * t + 999.0 * t * t) + 0.37 * (double)gs;
+        const float v = (float)(0.5 * sin(phase) + 0.05 * (double)u);
+        const size_t o = layout == AIDAX_LAYOUT_PLANAR ? (size_t)s * stride + k : (size_t)k * stride + s;
+        out[o] = v;
+    }
+}
+
 template <typename F>
 cudaError_t best_of(int millis, double work_per_launch, double* best_out, F launch)
 {
@@ -159,6 +188,17 @@ cudaError_t best_of(int millis, double work_per_launch, double* best_out, F laun
 }
 
 } // namespace
+
+extern "C" int aidax_generate_input(int device, void* cuda_stream, float* d_out, int first_stream, int n_streams, long long start_sample, int n_samples,
+                                    int layout, size_t stride, uint32_t seed)
+{
+    if (!d_out || n_streams <= 0 || n_samples <= 0 || (layout != AIDAX_LAYOUT_PLANAR && layout != AIDAX_LAYOUT_INTERLEAVED)) return AIDAX_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return AIDAX_ERR_CUDA;
+    const long long total = (long long)n_streams * n_samples;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 32);
+    gen_input_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(d_out, first_stream, n_streams, start_sample, n_samples, layout, stride, seed);
+    return cudaGetLastError() == cudaSuccess ? AIDAX_OK : AIDAX_ERR_CUDA;
+}
 
 extern "C" int aidax_measure_pipe_peaks(int device, int millis, double out[8])
 {

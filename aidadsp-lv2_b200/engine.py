@@ -247,6 +247,13 @@ class Engine:
     def synchronize(self):
         self._chk(self.lib.aidax_engine_synchronize(self.h))
 
+    def generate_input(self, d_out, n_streams, n_samples, start=0, first=0, layout=LAYOUT_INTERLEAVED, stride=None, seed=0, device=0):
+        """Device-side synthetic input (bench support, kernel K6) into the device pointer d_out, on the engine's stream."""
+        if stride is None:
+            stride = n_streams if layout == LAYOUT_INTERLEAVED else n_samples
+        self.lib.aidax_generate_input.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_size_t, C.c_uint32]
+        self._chk(self.lib.aidax_generate_input(device, self.cuda_stream, d_out, first, n_streams, start, n_samples, layout, stride, seed))
+
 
 def measure_pcie(device=0, nbytes=256 << 20):
     """Pinned-memory copy rates in GB/s: (H2D alone, D2H alone, per direction with both at once)."""

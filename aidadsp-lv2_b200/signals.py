@@ -30,3 +30,28 @@ def triangle(period_s, n_buffers, buffer=128, phase=0.0, fs=FS):
     """Slow triangle automation in [0,1] sampled once per buffer (C3's PARAM1/PARAM2)."""
     t = (np.arange(n_buffers) * buffer / fs) / period_s + phase
     return (2.0 * np.abs(t - np.floor(t + 0.5))).astype(np.float32)
+
+
+def _hash32(x):
+    x = x.astype(np.uint32)
+    x ^= x >> np.uint32(16); x *= np.uint32(0x7feb352d); x ^= x >> np.uint32(15); x *= np.uint32(0x846ca68b); x ^= x >> np.uint32(16)
+    return x
+
+
+def hash_noise_block(n_streams, n_samples, start=0, first_stream=0, seed=0):
+    """u(s, n) of the device-side generator (csrc/probes.cu: gen_input_kernel), bit for bit: [n_streams][n_samples] in [-1, 1)."""
+    with np.errstate(over="ignore"):
+        s = (np.arange(n_streams, dtype=np.uint64) + np.uint64(first_stream)).astype(np.uint32)[:, None]
+        n = (np.arange(n_samples, dtype=np.uint64) + np.uint64(start)).astype(np.uint32)[None, :]
+        h = _hash32(s * np.uint32(0x9E3779B1) + n * np.uint32(0x85EBCA77) + np.uint32(seed))
+    return (h >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -23) - np.float32(1.0)
+
+
+def sweep_hash_block(n_streams, n_samples, start=0, first_stream=0, seed=0, fs=FS):
+    """numpy mirror of aidax_generate_input: the sweep of SURVEY 8(d) with per-stream phase + 0.05 * hash noise, planar."""
+    n = np.arange(start, start + n_samples, dtype=np.float64)[None, :]
+    t = n / fs
+    gs = (np.arange(n_streams, dtype=np.float64) + first_stream)[:, None]
+    phase = 6.283185307179586 * (20.0 * t + 999.0 * t * t) + 0.37 * gs
+    u = hash_noise_block(n_streams, n_samples, start, first_stream, seed).astype(np.float64)
+    return (0.5 * np.sin(phase) + 0.05 * u).astype(np.float32)

@@ -147,9 +147,12 @@ def device_bench(wl, n_local, first_global, n_global, steps, warmup, device, til
     # input ring larger than L2 so every period's audio comes from HBM (timing hygiene)
     bytes_per_step = 2 * T * n_local * 4
     ring = max(2, min(steps + warmup, (2 * L2_BYTES + bytes_per_step - 1) // bytes_per_step))
-    base = torch.from_numpy(np.ascontiguousarray(signals.sweep_noise_block(min(n_local, 256), T).T)).to(dev)  # [T][<=256]
-    reps = (n_local + base.shape[1] - 1) // base.shape[1]
-    xin = [(base.repeat(1, reps)[:, :n_local] * (1.0 - 0.001 * i)).contiguous() for i in range(ring)]
+    # every stream gets its own input (sweep + noise with a per-stream phase and noise sequence), generated on the device
+    # (kernel K6, aidax_generate_input): ring buffer i holds samples [i*T, (i+1)*T) of all n_local streams, [T][n_local]
+    xin = [torch.empty((T, n_local), dtype=torch.float32, device=dev) for _ in range(ring)]
+    for i, x in enumerate(xin):
+        eng.generate_input(x.data_ptr(), n_local, T, start=i * T, first=first_global, layout=ax.LAYOUT_INTERLEAVED, seed=2024, device=device)
+    eng.synchronize()
     yout = [torch.empty_like(xin[0]) for _ in range(ring)]
     p1 = p2 = None
     if wl.automate_params:
@@ -273,6 +276,11 @@ def e2e_arm(args, wl, paths, n_inst, first_global, n_global, rank, world, local_
             pcie = tuple(float(v) for v in t.tolist())
     except Exception:
         pcie = None
+    if world > 1:   # every rank must take the same decisions below (the measurements inside them are collectives)
+        ok = torch.tensor([1 if pcie else 0], device=dev, dtype=torch.int64)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            pcie = None
 
     points = {}
 
@@ -296,6 +304,10 @@ def e2e_arm(args, wl, paths, n_inst, first_global, n_global, rank, world, local_
         if pcie:
             guess = int(0.8 * pcie[2] * 1e9 * period_s / (4 * T))
         n = max(CHUNK, min(n_inst, guess) // CHUNK * CHUNK)
+        if world > 1:
+            t = torch.tensor([n], device=dev, dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            n = int(t.item())
         best = None
         for _ in range(5):
             if n in points:
@@ -494,7 +506,7 @@ def run_ours(args, rank, world, local_rank):
            "ms_per_step": round(ms_per_step, 6), "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
            "dtype": "f32 (tf32x3 tensor-core gate GEMM, f64 biquad state)" if is_tc else "f32 (f64 biquad state)", "data": "synthetic",
            "config": {"workload": "%s: %s" % (wl.name.upper(), desc), "streams_per_gpu": n_local, "streams_total": n_global,
-                      "buffer": T, "sample_rate": FS, "layout": "stream-interleaved [128][N] in HBM",
+                      "buffer": T, "sample_rate": FS, "layout": "stream-interleaved [128][N] in HBM", "input": "per-stream sweep + noise generated on the device (aidax_generate_input)",
                       "l2": "input/output ring of %d buffer pairs (%.0f MiB) > L2, fresh buffer every step" % (ring_pairs, ring_pairs * 2 * T * n_local * 4 / 2**20),
                       "tile_mode": args.tile_mode,
                       "parallelism": ("fixed total of %d streams cut into contiguous shards over %d GPU(s), no collective" if strong else "%d streams per GPU, streams sharded over %d GPU(s), no collective") % (n_global if strong else n_local, world)},
@@ -657,6 +669,8 @@ def main():
     # stdout carries exactly ONE line: rank 0's JSON.  Native libraries write there too (NCCL prints its version banner
     # on communicator creation, the reference prints layer info while parsing models), so file descriptor 1 is pointed
     # at stderr for the whole run and the JSON line goes to the saved descriptor.
+    # a heterogeneous period launches up to 14 kernel families on as many CUDA streams: give them hardware queues of their own
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     global _JSON_FD
     sys.stdout.flush()
     _JSON_FD = os.dup(1)

@@ -241,6 +241,14 @@ void aidax_host_free(void* p);
  * FFMA) of `device`, measured with a register-resident FFMA loop over all SMs for about `millis` ms. */
 int aidax_measure_fp32_peak(int device, int millis, double* tflops_out);
 
+/* Bench support (kernel K6): synthetic input generated on the device, so that a measurement's audio never
+ * crosses PCIe.  x[s][n] = 0.5 sin(2 pi (20 t + 999 t^2) + 0.37 s) + 0.05 u(s, n), t = n / 48000 (the 20 Hz -> 20 kHz sweep of
+ * SURVEY 8(d) plus counter-based uniform noise; aidadsp_lv2_b200.signals.sweep_hash_block is the bit-exact numpy mirror of
+ * the noise and agrees with the sweep to one float rounding).  Rows/columns as in aidax_render_device; enqueued on
+ * `cuda_stream` (e.g. aidax_engine_cuda_stream) of `device`. */
+int aidax_generate_input(int device, void* cuda_stream, float* d_out, int first_stream, int n_streams, long long start_sample, int n_samples,
+                         int layout, size_t stride, uint32_t seed);
+
 /* Measured denominators for every pipe the chain kernels load (csrc/probes.cu), each from a register/shared-memory
  * resident saturating loop run for about millis/7 ms:
  *   out[0] FP32 FFMA TFLOP/s   out[1] XU MUFU.EX2 G lane-ops/s   out[2] FP64 DFMA TFLOP/s

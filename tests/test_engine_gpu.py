@@ -209,3 +209,24 @@ def test_block_size_invariance(native_libs, bundled_models, tile_mode):
         eng.close()
     assert np.isfinite(outs["regular"]).all() and np.abs(outs["regular"]).max() > 1e-3
     assert np.array_equal(outs["regular"], outs["ragged"]), np.abs(outs["regular"] - outs["ragged"]).max(axis=1)
+
+
+def test_device_input_generator_matches_numpy_mirror(native_libs):
+    """Kernel K6 (bench support): the device-side sweep + noise generator against its numpy mirror, both layouts, an offset
+    in time and in stream ids.  The hash noise is bit-exact; the sweep is evaluated in double on both sides and rounded
+    once, so the sum may differ by one float rounding at most."""
+    import torch
+    from aidadsp_lv2_b200 import signals
+    eng = ax.Engine(max_streams=64, max_block=128)
+    n, T, start, first, seed = 777, 128, 480000 - 64, 1000, 99
+    ref = signals.sweep_hash_block(n, T, start=start, first_stream=first, seed=seed)          # [n][T]
+    xi = torch.empty((T, n), dtype=torch.float32, device="cuda")
+    eng.generate_input(xi.data_ptr(), n, T, start=start, first=first, layout=ax.LAYOUT_INTERLEAVED, seed=seed)
+    xp = torch.empty((n, T + 5), dtype=torch.float32, device="cuda").fill_(7.0)
+    eng.generate_input(xp.data_ptr(), n, T, start=start, first=first, layout=ax.LAYOUT_PLANAR, stride=T + 5, seed=seed)
+    eng.synchronize()
+    a, b = xi.cpu().numpy().T, xp.cpu().numpy()
+    assert np.array_equal(a, b[:, :T]) and (b[:, T:] == 7.0).all()
+    assert np.abs(a - ref).max() <= 1.2e-7 and (a == ref).mean() > 0.99
+    assert 0.45 < np.abs(a).max() <= 0.55
+    eng.close()
