@@ -669,8 +669,6 @@ def main():
     # stdout carries exactly ONE line: rank 0's JSON.  Native libraries write there too (NCCL prints its version banner
     # on communicator creation, the reference prints layer info while parsing models), so file descriptor 1 is pointed
     # at stderr for the whole run and the JSON line goes to the saved descriptor.
-    # a heterogeneous period launches up to 14 kernel families on as many CUDA streams: give them hardware queues of their own
-    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     global _JSON_FD
     sys.stdout.flush()
     _JSON_FD = os.dup(1)
