@@ -160,7 +160,7 @@ struct aidax_engine {
     cudaEvent_t ev_fork = nullptr;
     cudaEvent_t ev_fan_fork = nullptr, ev_fan_join[kMaxKernelStreams] = {}; // family fan-out inside one range (launch_all)
     int fan_next = 0;
-    std::vector<cudaEvent_t> ev_in, ev_done, ev_out, ev_fam;
+    std::vector<cudaEvent_t> ev_in, ev_done, ev_out;
     bool pipeline_families = true; // AIDAX_PIPELINE_FAMILIES=0: deferred ranges wait for every copy-in and copy out after every kernel
     int grade_unit = 4096, grade_mid = 16384; // piece sizes of aidax_render_host_submit_graded (AIDAX_GRADE_UNIT / AIDAX_GRADE_MID)
     bool defer_hetero = true; // AIDAX_DEFER_HETERO=0: render heterogeneous hand-over ranges one by one (submit_range)
@@ -648,7 +648,6 @@ int aidax_engine_destroy(aidax_engine* e)
     for (cudaEvent_t ev : e->ev_in) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->ev_done) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->ev_out) cudaEventDestroy(ev);
-    for (cudaEvent_t ev : e->ev_fam) cudaEventDestroy(ev);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_fan_fork) cudaEventDestroy(e->ev_fan_fork);
     for (cudaEvent_t ev : e->ev_fan_join) if (ev) cudaEventDestroy(ev);
@@ -1169,7 +1168,6 @@ static int flush_deferred(aidax_engine* e)
     for (size_t i = 0; i < e->pending.size(); ++i) if (e->pending[i].deferred) order.push_back(i);
     if (order.empty()) return AIDAX_OK;
     std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return e->pending[a].first < e->pending[b].first; });
-    size_t fam_ev = 0;
     for (size_t a = 0; a < order.size();) {
         size_t b = a + 1;
         const aidax_engine::PendingRange& r0 = e->pending[order[a]];
@@ -1193,21 +1191,16 @@ static int flush_deferred(aidax_engine* e)
         };
         hooks.after = [&](const LaunchPlan& lp, cudaStream_t ls) -> int {
             if (!per_family) return AIDAX_OK;
-            while (e->ev_fam.size() <= fam_ev) {
-                cudaEvent_t ev;
-                CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-                e->ev_fam.push_back(ev);
-            }
-            CUDA_TRY(cudaEventRecord(e->ev_fam[fam_ev], ls));
-            CUDA_TRY(cudaStreamWaitEvent(e->stream_out, e->ev_fam[fam_ev], 0));
-            ++fam_ev;
+            // The family's streams go home on the family's OWN kernel stream, right behind its kernel: on one shared
+            // copy-out stream the copies would queue in launch order, and the launches go out largest-footprint first
+            // (build_plan), i.e. slowest first -- every small family's output would wait for the LSTM-40 kernel.
             for (const auto& run : lp.runs)
                 for (size_t k = a; k < b; ++k) { // a run of streams may cross hand-over ranges: their host rows need not be adjacent
                     const aidax_engine::PendingRange& r = e->pending[order[k]];
                     const int lo = std::max(run.first, r.first), hi = std::min(run.second, r.first + r.n);
                     if (hi <= lo) continue;
                     CUDA_TRY(cudaMemcpyAsync(r.out + (size_t)(lo - r.first) * row, e->d_io_out.d + (size_t)lo * (size_t)e->max_block, (size_t)(hi - lo) * row * sizeof(float),
-                                             cudaMemcpyDeviceToHost, e->stream_out));
+                                             cudaMemcpyDeviceToHost, ls));
                 }
             return AIDAX_OK;
         };

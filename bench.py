@@ -51,6 +51,7 @@ FS = 48000
 L2_BYTES = 126 * 1024 * 1024
 CAPACITY_STREAMS = 378880   # 5 x 592 CTAs x 128 streams: whole waves of chain_kernel_tc<LSTM,16> (4 CTAs/SM x 148 SMs)
 CHUNK = 16384               # instances per hand-over range of the plugin path (AIDAX_BATCH_CHUNK default)
+GRAIN = 4096                # granularity of the end-to-end instance-count search
 NORTH_STAR_SHARE = 125000   # 1 M streams per 8-GPU box
 METRIC = "stream-samples/s through the full rt-neural-generic chain, LSTM-16 (real-time 48 kHz streams = value/48000; us per 128-sample buffer in us_per_buffer)"
 
@@ -295,7 +296,7 @@ def e2e_arm(args, wl, paths, n_inst, first_global, n_global, rank, world, local_
     if args.e2e_streams:
         n_rt = min(n_inst, args.e2e_streams)
         point(n_rt, args.e2e_steps)
-    elif args.scaling == "strong" or n_inst <= CHUNK or args.workload != "c2" or args.streams:
+    elif args.scaling == "strong" or n_inst <= GRAIN or args.workload != "c2" or args.streams:
         n_rt = n_inst   # a configuration with a given stream count is measured at that count
         point(n_rt, args.e2e_steps)
     else:
@@ -303,7 +304,7 @@ def e2e_arm(args, wl, paths, n_inst, first_global, n_global, rank, world, local_
         guess = n_inst
         if pcie:
             guess = int(0.8 * pcie[2] * 1e9 * period_s / (4 * T))
-        n = max(CHUNK, min(n_inst, guess) // CHUNK * CHUNK)
+        n = max(GRAIN, min(n_inst, guess) // GRAIN * GRAIN)
         if world > 1:
             t = torch.tensor([n], device=dev, dtype=torch.int64)
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
@@ -316,7 +317,7 @@ def e2e_arm(args, wl, paths, n_inst, first_global, n_global, rank, world, local_
             if mean_s <= period_s and (best is None or n > best):
                 best = n
             scale = target / mean_s
-            nxt = max(CHUNK, min(n_inst, int(n * scale)) // CHUNK * CHUNK)
+            nxt = max(GRAIN, min(n_inst, int(n * scale)) // GRAIN * GRAIN)
             if world > 1:   # every rank renders the same count
                 t = torch.tensor([nxt], device=dev, dtype=torch.int64)
                 dist.all_reduce(t, op=dist.ReduceOp.MIN)
@@ -327,8 +328,8 @@ def e2e_arm(args, wl, paths, n_inst, first_global, n_global, rank, world, local_
         n_rt = best if best is not None else min(points, key=lambda k: points[k]["us_per_buffer"])
         point(n_rt, args.e2e_steps)   # the reported measurement
         # real time means (nearly) every period: the reported count must also keep the 95th percentile inside the deadline
-        while (not points[n_rt]["meets_deadline"] or points[n_rt]["us_p95"] > period_s * 1e6) and n_rt > CHUNK:
-            n_rt -= CHUNK
+        while (not points[n_rt]["meets_deadline"] or points[n_rt]["us_p95"] > period_s * 1e6) and n_rt > GRAIN:
+            n_rt -= 2 * GRAIN if n_rt > 8 * GRAIN else GRAIN
             point(n_rt, args.e2e_steps)
     main = points[n_rt]
     # ---- the north-star share (1 M streams per 8-GPU box) and the full instance count, for the record
@@ -352,7 +353,7 @@ def e2e_arm(args, wl, paths, n_inst, first_global, n_global, rank, world, local_
            "steps": main["periods"], "realtime_streams": int(n_rt * world) if main["meets_deadline"] else int(main["samples_per_s"] // FS),
            "meets_deadline": main["meets_deadline"], "deadline_us": round(period_s * 1e6, 1), "phase_us": main["phase_us"],
            "selection": "largest multiple of %d instances per GPU whose mean AND 95th-percentile period stay inside the deadline (search: %s)" %
-                        (CHUNK, ", ".join("%d -> %.0f us" % (k, points[k]["us_per_buffer"]) for k in sorted(points))),
+                        (GRAIN, ", ".join("%d -> %.0f us" % (k, points[k]["us_per_buffer"]) for k in sorted(points))),
            "path": "aidax-batch-host -> #batch begin() -> run_block() over the instances (control-row scan; run() only for instances with events or changed "
                    "controls) -> each completed chunk of instances is shipped at once (aidax_render_host_submit: pinned H2D -> kernels -> D2H on separate "
                    "CUDA streams) -> end() waits" if bulk else "aidax-batch-host -> run() x N -> chunks shipped as they complete -> end() waits",
