@@ -109,7 +109,8 @@ struct aidax_engine {
     std::mutex mu;
     int tile_mode = 0, math_mode = 0;
     int tc_min_streams = 4096; // auto mode: families at least this large run on the tensor-core variant
-    int tc_gen = 2, tc2_split = -1, tc2_atmem = -1; // which tensor-core kernel generation / shape (see choose_variant)
+    int ts_max = 0;            // AIDAX_TS_MAX: cap of the sub-block length (measurement knob; results do not depend on it)
+    int tc_gen = 3, tc2_split = -1, tc2_atmem = -1; // which tensor-core kernel generation / shape (see choose_variant)
     int sm_count = 148;
     size_t smem_optin = 0, smem_per_sm = 0;
     uint64_t launches = 0;
@@ -357,10 +358,16 @@ static const KernelVariant* choose_variant(const aidax_engine* e, const Family& 
         // a two-tile shape of kernels_tc2.cuh where one is compiled for this hidden size (variants.cu lists only shapes that
         // beat the first generation), unless AIDAX_TC_GEN=1; AIDAX_TC2_SPLIT / AIDAX_TC2_ATMEM pick among several compiled
         // shapes (measurement builds), default = the first one listed
-        if (e->tc_gen == 2 && !fam.tc2.empty()) {
-            for (const KernelVariant* kv : fam.tc2)
-                if ((e->tc2_split < 0 || kv->L == e->tc2_split) && (e->tc2_atmem < 0 || kv->S == e->tc2_atmem)) return kv;
-            return fam.tc2.front();
+        // generation 3 = the warp-specialised shapes of kernels_tc3.cuh (S bit 2), generation 2 = the two-tile shapes
+        if (e->tc_gen >= 2 && !fam.tc2.empty()) {
+            for (int gen = e->tc_gen; gen >= 2; --gen) {
+                for (const KernelVariant* kv : fam.tc2)
+                    if (((kv->S & 4) != 0) == (gen == 3) && (e->tc2_split < 0 || kv->L == e->tc2_split) &&
+                        (e->tc2_atmem < 0 || (kv->S & 3) == (e->tc2_atmem & 3)))
+                        return kv;
+                for (const KernelVariant* kv : fam.tc2)
+                    if (((kv->S & 4) != 0) == (gen == 3)) return kv;
+            }
         }
         if (fam.tc) return fam.tc;
     }
@@ -488,7 +495,7 @@ static int launch_all(aidax_engine* e, cudaStream_t st, int first, int n, int n_
             }
         }
         // samples per shared-memory sub-block: as many as fit with the variant's target residency, capped at the period
-        int ts = n_samples;
+        int ts = e->ts_max > 0 ? std::min(n_samples, e->ts_max) : n_samples;
         const size_t budget = std::min(e->smem_optin, e->smem_per_sm / (size_t)kv->ctas_per_sm - 1024);
         auto smem_for = [&](int t) { return (size_t)(kv->fixed_smem_floats + kv->NW * kv->warp_smem_floats(t, lp.max_param_tiles)) * sizeof(float); };
         // halving steps with the 3/4 points in between (128, 96, 64, 48, 32, 24, 16, 12, 8): results do not depend on ts
@@ -585,7 +592,8 @@ int aidax_engine_create(int device, int max_streams, int max_block, aidax_engine
     e->smem_optin = prop.sharedMemPerBlockOptin;
     e->smem_per_sm = prop.sharedMemPerMultiprocessor;
     if (const char* v = std::getenv("AIDAX_TC_MIN_STREAMS")) e->tc_min_streams = std::atoi(v);
-    if (const char* v = std::getenv("AIDAX_TC_GEN")) e->tc_gen = std::atoi(v) == 1 ? 1 : 2;
+    if (const char* v = std::getenv("AIDAX_TC_GEN")) e->tc_gen = std::min(3, std::max(1, std::atoi(v)));
+    if (const char* v = std::getenv("AIDAX_TS_MAX")) e->ts_max = std::atoi(v);
     if (const char* v = std::getenv("AIDAX_TC2_SPLIT")) e->tc2_split = std::atoi(v);
     if (const char* v = std::getenv("AIDAX_TC2_ATMEM")) e->tc2_atmem = std::atoi(v);
     if (const char* v = std::getenv("AIDAX_TILE_MODE")) e->tile_mode = std::max(0, std::min(std::atoi(v), 3)); // initial kernel-shape choice (aidax_engine_configure overrides)

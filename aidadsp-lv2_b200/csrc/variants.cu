@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_tc2.cuh"
+#include "kernels_tc3.cuh"
 #include "kernels_w.cuh"
 #include "variants.h"
 
@@ -44,6 +45,22 @@ static int wsf_tc2(int ts, int np) { return Tc2Shape<H, SPLIT, ATM, PP>::warp_fl
         (const void*)&chain_kernel_tc2<CELL, Hh, SPL, ((ATM) & 1) != 0, ((ATM) & 2) == 0, RES, 1> },     \
       &wsf_tc2<Hh, SPL, ((ATM) & 1) != 0, ((ATM) & 2) == 0>, 3, (TC2_SHAPE(Hh, SPL, ATM)::fixed_floats() + 3) & ~3, RES, 256 }
 #define BOTH_TC2(Hh, SPL, ATM, RES) VT2(0, Hh, SPL, ATM, RES), VT2(1, Hh, SPL, ATM, RES)
+
+// warp-specialised tensor-core variants (kernels_tc3.cuh): two tiles of 128 streams per CTA, SPLIT recurrence warps per lane
+// quadrant + one filter warpgroup; RR / FR = registers per thread of the two roles after setmaxnreg.  L carries SPLIT,
+// S carries 5 (bit 0: A operand in tensor memory, bit 2: warp-specialised).
+#ifndef AIDAX_TC3_NFW
+#define AIDAX_TC3_NFW 8 // filter warps per CTA (4: two streams per lane, 8: one)
+#endif
+template <int H, int SPLIT>
+static int wsf_tc3(int ts, int np) { return Tc3Shape<H, SPLIT, AIDAX_TC3_NFW>::warp_floats(ts, np); }
+#define TC3_SHAPE(Hh, SPL) Tc3Shape<Hh, SPL, AIDAX_TC3_NFW>
+#define VT3(CELL, Hh, SPL, RR, FR, RES)                                                                  \
+    { CELL, Hh, SPL, 5, TC3_SHAPE(Hh, SPL)::NW, 256 / TC3_SHAPE(Hh, SPL)::NW,                            \
+      { (const void*)&chain_kernel_tc3<CELL, Hh, SPL, AIDAX_TC3_NFW, RR, FR, RES, 0>,                    \
+        (const void*)&chain_kernel_tc3<CELL, Hh, SPL, AIDAX_TC3_NFW, RR, FR, RES, 1> },                  \
+      &wsf_tc3<Hh, SPL>, 3, (TC3_SHAPE(Hh, SPL)::fixed_floats() + 3) & ~3, RES, 256 }
+#define BOTH_TC3(Hh, SPL, RR, FR, RES) VT3(0, Hh, SPL, RR, FR, RES), VT3(1, Hh, SPL, RR, FR, RES)
 
 #ifndef AIDAX_TC_NT32
 #define AIDAX_TC_NT32 3
@@ -90,6 +107,42 @@ static int wsf_w(int ts, int np) { return WShape::warp_floats(ts, np); }
 #define AIDAX_TC2_LIST_40 BOTH_TC2(40, 2, 3, 1),
 #endif
 
+// Warp-specialised shapes per hidden size (see kernels_tc3.cuh): (H, SPLIT, R registers, F registers, CTAs per SM)
+#ifndef AIDAX_TC3_RREG
+#define AIDAX_TC3_RREG (AIDAX_TC3_NFW == 8 ? 96 : 104)
+#endif
+#ifndef AIDAX_TC3_FREG
+#define AIDAX_TC3_FREG 32
+#endif
+// SPLIT 2 (one CTA of 640 threads per SM: 96 registers per thread at launch)
+#ifndef AIDAX_TC3_RREG2
+#define AIDAX_TC3_RREG2 104
+#endif
+#ifndef AIDAX_TC3_FREG2
+#define AIDAX_TC3_FREG2 (AIDAX_TC3_NFW == 8 ? 32 : 64)
+#endif
+#ifndef AIDAX_TC3_LIST_8
+#define AIDAX_TC3_LIST_8 BOTH_TC3(8, 1, AIDAX_TC3_RREG, AIDAX_TC3_FREG, 2),
+#endif
+#ifndef AIDAX_TC3_LIST_12
+#define AIDAX_TC3_LIST_12 BOTH_TC3(12, 1, AIDAX_TC3_RREG, AIDAX_TC3_FREG, 2),
+#endif
+#ifndef AIDAX_TC3_LIST_16
+#define AIDAX_TC3_LIST_16 BOTH_TC3(16, 1, AIDAX_TC3_RREG, AIDAX_TC3_FREG, 2),
+#endif
+#ifndef AIDAX_TC3_LIST_20
+#define AIDAX_TC3_LIST_20 BOTH_TC3(20, 1, AIDAX_TC3_RREG, AIDAX_TC3_FREG, 2),
+#endif
+#ifndef AIDAX_TC3_LIST_24
+#define AIDAX_TC3_LIST_24 // measured slower than generation 1 at GPU-filling counts (2040 vs 1961 us per 262144-stream period)
+#endif
+#ifndef AIDAX_TC3_LIST_32
+#define AIDAX_TC3_LIST_32 BOTH_TC3(32, 2, AIDAX_TC3_RREG2, AIDAX_TC3_FREG2, 1),
+#endif
+#ifndef AIDAX_TC3_LIST_40
+#define AIDAX_TC3_LIST_40 BOTH_TC3(40, 2, AIDAX_TC3_RREG2, AIDAX_TC3_FREG2, 1),
+#endif
+
 #define CAT_(a, b) a##b
 #define CAT(a, b) CAT_(a, b)
 
@@ -97,19 +150,19 @@ const KernelVariant CAT(kVariantsH, AIDAX_VARIANT_H)[] = {
 #if AIDAX_VARIANT_H == 0
     V(2, 8, 8, 8, 4),
 #elif AIDAX_VARIANT_H == 8
-    BOTH_W(8, 4), BOTH(8, 8, 1, 4), BOTH(8, 8, 4, 4), BOTH(8, 8, 8, 4), BOTH_TC(8, 1, 4), AIDAX_TC2_LIST_8
+    BOTH_W(8, 4), BOTH(8, 8, 1, 4), BOTH(8, 8, 4, 4), BOTH(8, 8, 8, 4), BOTH_TC(8, 1, 4), AIDAX_TC2_LIST_8 AIDAX_TC3_LIST_8
 #elif AIDAX_VARIANT_H == 12
-    BOTH_W(12, 4), BOTH(12, 4, 1, 4), BOTH(12, 4, 2, 4), BOTH(12, 4, 4, 4), BOTH_TC(12, 1, 4), AIDAX_TC2_LIST_12
+    BOTH_W(12, 4), BOTH(12, 4, 1, 4), BOTH(12, 4, 2, 4), BOTH(12, 4, 4, 4), BOTH_TC(12, 1, 4), AIDAX_TC2_LIST_12 AIDAX_TC3_LIST_12
 #elif AIDAX_VARIANT_H == 16
-    BOTH_W(16, 4), BOTH(16, 16, 1, 4), BOTH(16, 16, 4, 4), BOTH(16, 8, 8, 4), BOTH_TC(16, 1, AIDAX_TC_RES16), AIDAX_TC2_LIST_16
+    BOTH_W(16, 4), BOTH(16, 16, 1, 4), BOTH(16, 16, 4, 4), BOTH(16, 8, 8, 4), BOTH_TC(16, 1, AIDAX_TC_RES16), AIDAX_TC2_LIST_16 AIDAX_TC3_LIST_16
 #elif AIDAX_VARIANT_H == 20
-    BOTH(20, 4, 1, 4), BOTH(20, 4, 2, 4), BOTH(20, 4, 4, 4), BOTH_TC(20, 1, 3), AIDAX_TC2_LIST_20
+    BOTH(20, 4, 1, 4), BOTH(20, 4, 2, 4), BOTH(20, 4, 4, 4), BOTH_TC(20, 1, 3), AIDAX_TC2_LIST_20 AIDAX_TC3_LIST_20
 #elif AIDAX_VARIANT_H == 24
-    BOTH(24, 8, 1, 4), BOTH(24, 8, 4, 4), BOTH(24, 8, 8, 4), BOTH_TC(24, 1, 3), AIDAX_TC2_LIST_24
+    BOTH(24, 8, 1, 4), BOTH(24, 8, 4, 4), BOTH(24, 8, 8, 4), BOTH_TC(24, 1, 3), AIDAX_TC2_LIST_24 AIDAX_TC3_LIST_24
 #elif AIDAX_VARIANT_H == 32
-    BOTH(32, 32, 1, 4), BOTH(32, 16, 4, 4), BOTH(32, 8, 4, 4), BOTH_TC(32, AIDAX_TC_NT32, 1), AIDAX_TC2_LIST_32
+    BOTH(32, 32, 1, 4), BOTH(32, 16, 4, 4), BOTH(32, 8, 4, 4), BOTH_TC(32, AIDAX_TC_NT32, 1), AIDAX_TC2_LIST_32 AIDAX_TC3_LIST_32
 #elif AIDAX_VARIANT_H == 40
-    BOTH(40, 8, 1, 4), BOTH(40, 8, 2, 4), BOTH(40, 8, 4, 4), BOTH_TC(40, AIDAX_TC_NT40, 1), AIDAX_TC2_LIST_40
+    BOTH(40, 8, 1, 4), BOTH(40, 8, 2, 4), BOTH(40, 8, 4, 4), BOTH_TC(40, AIDAX_TC_NT40, 1), AIDAX_TC2_LIST_40 AIDAX_TC3_LIST_40
 #elif AIDAX_VARIANT_H == 64
     BOTH(64, 32, 1, 4), BOTH(64, 32, 4, 4), BOTH(64, 16, 4, 4),
 #elif AIDAX_VARIANT_H == 80
