@@ -495,7 +495,11 @@ static int launch_all(aidax_engine* e, cudaStream_t st, int first, int n, int n_
             }
         }
         // samples per shared-memory sub-block: as many as fit with the variant's target residency, capped at the period
-        int ts = e->ts_max > 0 ? std::min(n_samples, e->ts_max) : n_samples;
+        // the warp-specialised shapes pipeline sub-blocks between their filter and recurrence warps: shorter sub-blocks
+        // shorten the pipeline's fill and drain (measured on B200: 16 beats 32 and 8 for every hidden size up to 20,
+        // 8..16 are level for H 32/40)
+        const int ts_cap = e->ts_max > 0 ? e->ts_max : ((kv->kind == 3 && (kv->S & 4)) ? 16 : 0);
+        int ts = ts_cap > 0 ? std::min(n_samples, ts_cap) : n_samples;
         const size_t budget = std::min(e->smem_optin, e->smem_per_sm / (size_t)kv->ctas_per_sm - 1024);
         auto smem_for = [&](int t) { return (size_t)(kv->fixed_smem_floats + kv->NW * kv->warp_smem_floats(t, lp.max_param_tiles)) * sizeof(float); };
         // halving steps with the 3/4 points in between (128, 96, 64, 48, 32, 24, 16, 12, 8): results do not depend on ts
@@ -832,6 +836,66 @@ int aidax_model_check_json(const char* path, aidax_model_desc* out)
     } catch (const std::exception& ex) {
         return fail(AIDAX_ERR_MODEL, "Unable to load json file: %s Error: %s", path, ex.what());
     }
+    return AIDAX_OK;
+}
+
+// The reference's load-time sanity check (RtNeuralGeneric::testModel, rt-neural-generic.cpp:900-955; compiled into DEBUG
+// builds at :1066-1073): the network alone over the file's `input_batch`, gains forced to 1, both parameters at 0, from
+// reset(), compared sample by sample with `output_batch` at TEST_MODEL_THR = 1e-5 (rt-neural-generic.h:182).  Here it runs
+// on the GPU through the ordinary render path (a scratch stream bound to a gain-less copy of the model), so it checks what
+// the kernels of THIS engine configuration compute for this capture.
+int aidax_model_selftest(aidax_engine* e, int model_id, float* max_err_out, int* n_errs_out, int* n_samples_out)
+{
+    if (!e) return fail(AIDAX_ERR_ARG, "null engine");
+    HostModel hm;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        if (model_id < 0 || model_id >= (int)e->models.size() || !e->models[model_id].d_weights) return fail(AIDAX_ERR_ARG, "unknown model %d", model_id);
+        hm = e->models[model_id].host;
+    }
+    if (hm.test_in.empty()) return fail(AIDAX_ERR_STATE, "model %d carries no input_batch / output_batch", model_id);
+    const std::vector<float> x = hm.test_in, want = hm.test_out;
+    hm.desc.in_gain = 1.0f;  // "Gain correction inject unwanted errors" (:903-907)
+    hm.desc.out_gain = 1.0f;
+    hm.test_in.clear(); hm.test_out.clear();
+    int tmp_model = -1, s = -1;
+    int rc = register_host_model(e, std::move(hm), std::string(), &tmp_model);
+    if (rc) return rc;
+    std::vector<float> y(x.size(), 0.f);
+    rc = aidax_stream_open(e, 48000.0, &s);
+    if (rc == AIDAX_OK) {
+        float c[AIDAX_N_CONTROLS] = {};
+        c[AIDAX_CTRL_EQBYPASS] = 1.0f;   // the network alone: no in_lpf, no EQ, no dc blocker, unity gains
+        c[AIDAX_CTRL_ENABLED] = 1.0f;
+        c[AIDAX_CTRL_BFREQ] = 305.0f; c[AIDAX_CTRL_MFREQ] = 750.0f; c[AIDAX_CTRL_MIDQ] = 0.707f; c[AIDAX_CTRL_TFREQ] = 2000.0f;
+        rc = aidax_stream_set_model(e, s, tmp_model, 0.f, 0.f);  // "Conditioned models tested with all params at 0" (:908-916)
+        if (rc == AIDAX_OK) rc = aidax_stream_set_controls(e, s, c, 0);
+        const int blk = std::min(e->max_block, 128);
+        std::vector<float> zero((size_t)blk, 0.f), sink((size_t)blk, 0.f);
+        // one silent period executes the stream's commands (open, model binding incl. its pre-warm) ...
+        if (rc == AIDAX_OK) rc = aidax_render_host(e, s, 1, blk, zero.data(), sink.data(), AIDAX_LAYOUT_PLANAR, (size_t)blk);
+        // ... then the test starts from reset() with the gain ramps at their targets
+        const std::vector<float> z((size_t)kMaxHidden, 0.f);
+        if (rc == AIDAX_OK) rc = aidax_stream_set_state(e, s, z.data(), z.data(), nullptr);
+        if (rc == AIDAX_OK) rc = aidax_stream_activate(e, s);
+        for (size_t off = 0; off < x.size() && rc == AIDAX_OK; off += (size_t)e->max_block) {
+            const int n = (int)std::min<size_t>((size_t)e->max_block, x.size() - off);
+            rc = aidax_render_host(e, s, 1, n, x.data() + off, y.data() + off, AIDAX_LAYOUT_PLANAR, (size_t)n);
+        }
+        aidax_stream_close(e, s);
+    }
+    aidax_model_release(e, tmp_model);
+    if (rc) return rc;
+    float max_err = 0.f;
+    int n_errs = 0;
+    for (size_t i = 0; i < x.size(); ++i) {
+        const float err = std::fabs(y[i] - want[i]);
+        max_err = std::max(max_err, err);
+        if ((double)err > 1.0e-5) ++n_errs; // TEST_MODEL_THR
+    }
+    if (max_err_out) *max_err_out = max_err;
+    if (n_errs_out) *n_errs_out = n_errs;
+    if (n_samples_out) *n_samples_out = (int)x.size();
     return AIDAX_OK;
 }
 

@@ -28,6 +28,8 @@ struct HostModel {
     std::vector<float> dense_w; // [H]
     float dense_b = 0.f;
     std::string path;
+    // the exporter's self-test vectors, when the file holds them (testModel, rt-neural-generic.cpp:900-955, 1066-1073)
+    std::vector<float> test_in, test_out;
 };
 
 inline bool hidden_size_supported(int h)
@@ -118,6 +120,18 @@ inline HostModel parse_model_json(const std::string& text)
     const JsonValue& db = dw.at((size_t)1);
     if (!db.is_array() || db.size() < 1) throw std::out_of_range("dense bias missing");
     m.dense_b = db.at((size_t)0).as_float();
+
+    if (j["input_batch"].is_array() && j["output_batch"].is_array()) {
+        const JsonValue& xi = j["input_batch"];
+        const JsonValue& yo = j["output_batch"];
+        const size_t n = std::min(xi.size(), yo.size());
+        m.test_in.resize(n);
+        m.test_out.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            m.test_in[i] = xi.at(i).as_float();
+            m.test_out[i] = yo.at(i).as_float();
+        }
+    }
     return m;
 }
 

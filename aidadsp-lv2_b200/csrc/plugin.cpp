@@ -776,6 +776,16 @@ LV2_Worker_Status work(LV2_Handle instance, LV2_Worker_Respond_Function respond,
         int model_id = -1, input_size = 0;
         if (aidax_model_load_json(self->engine, path, &model_id, &input_size) == AIDAX_OK) {
             lv2_log_note(&self->logger, "Successfully loaded json file: %s\n", path);
+            // the reference's DEBUG builds run testModel here (:1066-1073, 900-955); opt-in: AIDAX_SELFTEST=1
+            static const bool selftest = std::getenv("AIDAX_SELFTEST") != nullptr && std::atoi(std::getenv("AIDAX_SELFTEST")) != 0;
+            if (selftest) {
+                float max_err = 0.f;
+                int n_errs = 0, n = 0;
+                if (aidax_model_selftest(self->engine, model_id, &max_err, &n_errs, &n) == AIDAX_OK) {
+                    lv2_log_trace(&self->logger, "%s testModel: %d errs!\n", n_errs ? "Failure" : "Success", n_errs);
+                    lv2_log_trace(&self->logger, "Max err: %.12f, thr: %.12f\n", max_err, 1.0e-5);
+                }
+            }
             LoadedModel* m = new LoadedModel{model_id, input_size, strdup(path), p1, p2};
             // "cache input size for later" (:1082): published before the swap, as in the reference; the next run() writes
             // it to the ModelInSize port (the latched row no longer matches the port, so run_block takes the long way)

@@ -65,6 +65,7 @@ def load_library():
     lib.aidax_model_load_json.argtypes = [vp, C.c_char_p, ip, ip]
     lib.aidax_model_describe.argtypes = [vp, C.c_int, C.POINTER(ModelDesc)]
     lib.aidax_model_release.argtypes = [vp, C.c_int]
+    lib.aidax_model_selftest.argtypes = [vp, C.c_int, fp, ip, ip]
     lib.aidax_engine_pci_bus_id.argtypes = [vp, C.c_char_p, C.c_int]
     lib.aidax_stream_open.argtypes = [vp, C.c_double, ip]
     lib.aidax_stream_close.argtypes = [vp, C.c_int]
@@ -173,6 +174,12 @@ class Engine:
         buf = C.create_string_buffer(64)
         self._chk(self.lib.aidax_engine_pci_bus_id(self.h, buf, 64))
         return buf.value.decode()
+
+    def selftest_model(self, mid):
+        """The reference's load-time testModel on the GPU: (max abs error, samples above 1e-5, samples compared)."""
+        err, bad, n = C.c_float(0), C.c_int(0), C.c_int(0)
+        self._chk(self.lib.aidax_model_selftest(self.h, mid, C.byref(err), C.byref(bad), C.byref(n)))
+        return err.value, bad.value, n.value
 
     def describe_model(self, mid):
         d = ModelDesc()

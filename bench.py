@@ -49,7 +49,7 @@ sys.path.insert(0, ROOT)
 T = 128
 FS = 48000
 L2_BYTES = 126 * 1024 * 1024
-CAPACITY_STREAMS = 378880   # 5 x 592 CTAs x 128 streams: whole waves of chain_kernel_tc<LSTM,16> (4 CTAs/SM x 148 SMs)
+CAPACITY_STREAMS = 378880   # 5 x 296 CTAs x 256 streams: whole waves of chain_kernel_tc3<LSTM,16> (2 CTAs/SM x 148 SMs)
 CHUNK = 16384               # instances per hand-over range of the plugin path (AIDAX_BATCH_CHUNK default)
 GRAIN = 4096                # granularity of the end-to-end instance-count search
 NORTH_STAR_SHARE = 125000   # 1 M streams per 8-GPU box
@@ -206,7 +206,7 @@ def timed_device_steps(eng, ext, step, steps, warmup, dev, world, dist):
 def kernel_name(wl, n_local, tile_mode):
     m = wl.models[0]
     tc = m.hidden <= 40 and (tile_mode == 3 or (tile_mode == 0 and n_local >= 4096))
-    return ("chain_kernel_tc (fused chain + tcgen05 3xTF32 gate GEMM in TMEM, thread-per-stream gate epilogue)" if tc
+    return ("chain_kernel_tc3 (fused chain, warp-specialised: recurrence warps with the tcgen05 3xTF32 gate GEMM in TMEM and a thread-per-stream gate epilogue, filter warps one sub-block ahead/behind over a shared-memory ring)" if tc
             else "chain_kernel_w / chain_kernel (fused chain + FP32 recurrence: warp-per-stream latency shape for small batches, register-tiled shapes above)"), tc
 
 

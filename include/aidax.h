@@ -146,6 +146,14 @@ int aidax_model_load_json(aidax_engine* e, const char* path, int* model_id_out, 
  * valid for the life of the engine. */
 int aidax_model_release(aidax_engine* e, int model_id);
 
+/* Opt-in load-time check: the reference's testModel (rt-neural-generic.cpp:900-955, called from loadModelFromPath at
+ * :1066-1073 in DEBUG builds).  Renders the `input_batch` the model file carries through the network alone (gains 1,
+ * PARAM1/2 = 0, state reset) on the GPU, in the engine's current kernel configuration, and compares it with the file's
+ * `output_batch`: *n_errs_out = samples off by more than TEST_MODEL_THR = 1e-5 (rt-neural-generic.h:182), *max_err_out
+ * the largest difference.  Needs one free stream slot.  AIDAX_ERR_STATE when the file held no vectors (or the model
+ * was registered from arrays). */
+int aidax_model_selftest(aidax_engine* e, int model_id, float* max_err_out, int* n_errs_out, int* n_samples_out);
+
 int aidax_model_describe(aidax_engine* e, int model_id, aidax_model_desc* out);
 
 /* Host-only (no GPU needed): parse + validate a model file with the rules above and report what

@@ -187,3 +187,24 @@ def test_model_file_is_read_again_after_a_re_export(native_libs, tmp_path):
     with pytest.raises(ax.AidaxError):
         eng.release_model(a)
     eng.close()
+
+
+def test_load_time_selftest_on_the_gpu(native_libs, bundled_models):
+    """The reference's testModel (rt-neural-generic.cpp:900-955) as an opt-in engine check: every bundled capture's
+    input_batch rendered on the GPU, compared with its output_batch at the reference's own 1e-5 (precise gate math;
+    the fast gates are held to the 2e-5 of tests/test_engine_gpu.py)."""
+    for math_mode, tol, allow_errs in ((1, 1e-5, 0), (0, 2e-5, None)):
+        eng = ax.Engine(max_streams=8, max_block=512)
+        eng.configure(tile_mode=0, math_mode=math_mode)
+        for p in bundled_models:
+            mid, _ = eng.load_json(p)
+            err, bad, n = eng.selftest_model(mid)
+            assert n == 2048 and err <= tol, (p, err, bad)
+            if allow_errs is not None:
+                assert bad == allow_errs, (p, err, bad)
+        # a model registered from arrays carries no vectors
+        from aidadsp_lv2_b200 import models as _m
+        mid = eng.register_model(_m.synthetic(0, 16, 1, seed=3))
+        with pytest.raises(ax.AidaxError):
+            eng.selftest_model(mid)
+        eng.close()
