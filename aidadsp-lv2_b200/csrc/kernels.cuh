@@ -87,9 +87,25 @@ struct BiquadReg {
         double* z = sa.bq_z + (size_t)which * 2 * cap + slot;
         z[0] = z1; z[cap] = z2;
     }
+    // float -> double is exact; WI = 1 builds the double with integer instructions instead of F2F.F64.F32, which runs on
+    // the XU pipe next to the gates' MUFU.EX2/RCP (the pipe that bounds the tensor-core kernels).  Zero, subnormal, infinite
+    // and NaN inputs (exponent field 0 or 255) take the conversion instruction, so every input maps to the same double.
+    template <int WI>
+    __device__ __forceinline__ static double widen(float in)
+    {
+        if constexpr (WI == 0) {
+            return (double)in;
+        } else {
+            const uint32_t b = __float_as_uint(in);
+            if ((((b >> 23) + 1u) & 0xFEu) == 0u) return (double)in;
+            const uint32_t hi = (b & 0x80000000u) | (((b & 0x7FFFFFFFu) >> 3) + 0x38000000u);
+            return __hiloint2double((int)hi, (int)(b << 29));
+        }
+    }
+    template <int WI = 0>
     __device__ __forceinline__ float process(float in)
     {
-        const double x = (double)in;
+        const double x = widen<WI>(in);
         const double o = __dadd_rn(__dmul_rn(x, a0), z1);
         z1 = __dsub_rn(__dadd_rn(__dmul_rn(x, a1), z2), __dmul_rn(b1, o));
         z2 = __dsub_rn(__dmul_rn(x, a2), __dmul_rn(b2, o));
@@ -104,13 +120,13 @@ __device__ __forceinline__ float exp_smooth_next(float& mem, float coef, float t
     return mem;
 }
 
-template <int XP>
+template <int XP, int WI = 0>
 __device__ __forceinline__ void pass_biquad(float* xcol, int ts, const StreamArrays& sa, int which, int slot)
 {
     BiquadReg f;
     f.load(sa, which, slot);
 #pragma unroll 4
-    for (int t = 0; t < ts; ++t) xcol[t * XP] = f.process(xcol[t * XP]);
+    for (int t = 0; t < ts; ++t) xcol[t * XP] = f.template process<WI>(xcol[t * XP]);
     f.store(sa, which, slot);
 }
 
@@ -169,7 +185,7 @@ __device__ __forceinline__ void pass_eq(float* xcol, int ts, const StreamArrays&
 }
 
 // Stage 1+2 of run(): optional in_lpf then the pre-gain ramp (:622-627)
-template <int XP>
+template <int XP, int WI = 0>
 __device__ __forceinline__ void pass_lpf_pregain(float* xcol, int ts, const StreamArrays& sa, int slot, bool lpf_on)
 {
     const float coef = sa.exp_coef[slot];
@@ -180,7 +196,7 @@ __device__ __forceinline__ void pass_lpf_pregain(float* xcol, int ts, const Stre
         f.load(sa, BQ_INLPF, slot);
 #pragma unroll 4
         for (int t = 0; t < ts; ++t) {
-            const float x = f.process(xcol[t * XP]);
+            const float x = f.template process<WI>(xcol[t * XP]);
             xcol[t * XP] = __fmul_rn(x, exp_smooth_next(mem, coef, tgt));
         }
         f.store(sa, BQ_INLPF, slot);
@@ -193,7 +209,7 @@ __device__ __forceinline__ void pass_lpf_pregain(float* xcol, int ts, const Stre
 
 // Stage 7 (master ramp, :654-655), optionally preceded by the dc blocker (:645-650) when no
 // post-EQ sits between them.
-template <int XP>
+template <int XP, int WI = 0>
 __device__ __forceinline__ void pass_dc_master(float* xcol, int ts, const StreamArrays& sa, int slot, bool dc_on, bool master_on)
 {
     const float coef = sa.exp_coef[slot];
@@ -204,7 +220,7 @@ __device__ __forceinline__ void pass_dc_master(float* xcol, int ts, const Stream
 #pragma unroll 4
     for (int t = 0; t < ts; ++t) {
         float x = xcol[t * XP];
-        if (dc_on) x = f.process(x);
+        if (dc_on) x = f.template process<WI>(x);
         if (master_on) x = __fmul_rn(x, exp_smooth_next(mem, coef, tgt));
         xcol[t * XP] = x;
     }

@@ -62,6 +62,9 @@
 #ifndef AIDAX_POLY_EX2
 #define AIDAX_POLY_EX2 0
 #endif
+#ifndef AIDAX_POLY_PAIRS
+#define AIDAX_POLY_PAIRS 0
+#endif
 
 namespace aidax {
 
@@ -253,6 +256,27 @@ struct TcCell {
                                      __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23)));
         return tc::add2(r, tc::splat2(1.0f));
     }
+    // 2^-24 * (1 + 2^e) saturated at 1, like scaled_one_plus_exp2, with 2^e on the FMA pipe: the polynomial's coefficients carry
+    // the 2^-24 (exact), e is clamped to [-100, 24] so that the exponent arithmetic stays in the normal range
+    // (2^-100 vanishes next to 1; at 24 the sum saturates).
+    __device__ __forceinline__ static float2 scaled_one_plus_exp2_fma(float2 e)
+    {
+        constexpr float s = 5.9604644775390625e-08f;
+        const float2 ec = make_float2(fminf(fmaxf(e.x, -100.0f), 24.0f), fminf(fmaxf(e.y, -100.0f), 24.0f));
+        const float2 magic = tc::splat2(12582912.0f);
+        const float2 t = tc::add2(ec, magic);
+        const float2 f = tc::sub2(ec, tc::sub2(t, magic));
+        float2 p = tc::splat2(1.534581097e-04f * s);
+        p = tc::fma2(p, f, tc::splat2(1.339993090e-03f * s));
+        p = tc::fma2(p, f, tc::splat2(9.618489072e-03f * s));
+        p = tc::fma2(p, f, tc::splat2(5.550328642e-02f * s));
+        p = tc::fma2(p, f, tc::splat2(2.402264625e-01f * s));
+        p = tc::fma2(p, f, tc::splat2(6.931471825e-01f * s));
+        p = tc::fma2(p, f, tc::splat2(s));
+        const float rx = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));
+        const float ry = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
+        return make_float2(__saturatef(rx + s), __saturatef(ry + s));
+    }
     // site: 0 = input/forget/output (LSTM) or update/reset (GRU) gates, 1 = the LSTM candidate gate g,
     // 2 = tanh of the new cell state (LSTM) / of the candidate (GRU)
     template <int SITE>
@@ -356,7 +380,9 @@ struct TcCell {
                 const float2 c = tc::fma2(fi, make_float2(cst[u], cst[u + 1]), itg);
                 cst[u] = c.x;
                 cst[u + 1] = c.y;
-                ec[pr] = scaled_one_plus_exp2(tc::mul2(c, tc::splat2(2.f * L2E)));
+                // AIDAX_POLY_PAIRS: how many of the group's unit pairs take the tanh(c') exponential on the FMA pipe
+                if (pr < AIDAX_POLY_PAIRS) ec[pr] = scaled_one_plus_exp2_fma(tc::mul2(c, tc::splat2(2.f * L2E)));
+                else ec[pr] = scaled_one_plus_exp2(tc::mul2(c, tc::splat2(2.f * L2E)));
             }
             if constexpr (TWO) inv4(ec[0], ec[1], ec[2], ec[3], t[0], t[1], t[2], t[3]);
             else inv2(ec[0], ec[1], t[0], t[1]);

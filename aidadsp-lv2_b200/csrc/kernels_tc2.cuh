@@ -28,6 +28,36 @@
 
 namespace aidax {
 
+namespace tc {
+// Wait for a tile's MMA completion.  AIDAX_MMA_POLL_NS = 0: mbarrier.try_wait with a suspend-time hint (the warp parks, but
+// NANOSLEEP.SYNCS wakes on every mbarrier event of the CTA and re-issues the check: ~15 wake-ups of 5 instructions per
+// wait in the warp-specialised kernel); > 0: test_wait + a plain nanosleep of that length.
+#ifndef AIDAX_MMA_POLL_NS
+#define AIDAX_MMA_POLL_NS 0
+#endif
+__device__ __forceinline__ void mbar_wait_mma(uint32_t bar_addr, uint32_t parity)
+{
+#if AIDAX_MMA_POLL_NS > 0
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P1;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(bar_addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(AIDAX_MMA_POLL_NS);
+    }
+#else
+    mbar_wait(bar_addr, parity);
+#endif
+}
+} // namespace tc
+
 template <int H, int SPLIT, bool ATMEM, bool PP = true>
 struct Tc2Shape {
     using S = TcShape<H>;
@@ -262,7 +292,7 @@ struct Tc2Cell {
 #pragma unroll
             for (int g = 0; g < TPT; ++g) {
 #if !(AIDAX_WHATIF & 1)
-                tc::mbar_wait(tt[g].bar_addr, tt[g].phase);
+                tc::mbar_wait_mma(tt[g].bar_addr, tt[g].phase);
                 tt[g].phase ^= 1u;
 #endif
                 tc::tc_fence_after();

@@ -31,6 +31,32 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar_addr)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
+// Wait of a warp that is NOT on the critical path (the filter warps waiting for a sub-block to come back from the recurrence
+// warps): poll and sleep.  mbarrier.try_wait's suspended form (NANOSLEEP.SYNCS) wakes on every mbarrier event of the CTA --
+// here two MMA completions per time step -- and each wake-up re-issues the check: ncu counted 26 % of the kernel's executed
+// instructions in those retry loops, issue slots taken from the recurrence warps.
+#ifndef AIDAX_TC3_POLL_NS
+#define AIDAX_TC3_POLL_NS 1000
+#endif
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar_addr, uint32_t parity)
+{
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P1;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(bar_addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+#if AIDAX_TC3_POLL_NS > 0
+        __nanosleep(AIDAX_TC3_POLL_NS);
+#endif
+    }
+}
 template <int N>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
@@ -53,7 +79,7 @@ struct Tc3Shape {
     static constexpr int NBUF = 2;             // ring depth of the audio sub-block tiles
     static constexpr int YB = SPLIT > 1 ? SPLIT : 0;
     static constexpr int TILE_COLS = N + 2 * KP; // TMEM columns of one tile: accumulator | A hi | A lo
-    static constexpr int NBARS = 2 + 2 * 8 * NBUF; // MMA completion per tile, full / done per (warp-tile, ring slot)
+    static constexpr int NBARS = 2 + 2 * 8 * NBUF + 3; // MMA completion per tile, full / done per (warp-tile, ring slot), 3 CTA-wide rendezvous
     static_assert(H % SPLIT == 0 && UH % 4 == 0, "the units of a thread must be whole 16-column accumulator chunks");
     static_assert(2 * TILE_COLS <= 512, "two tiles must fit tensor memory");
 
@@ -71,10 +97,29 @@ struct Tc3Shape {
     __host__ __device__ static constexpr int warp_floats(int ts, int n_param_tiles) { return (NBUF * 8 * ts * XP * (1 + n_param_tiles + YB) + NW - 1) / NW; }
 };
 
+// Sub-block schedule of a period: the FIRST sub-block is short (AIDAX_TC3_TS0 samples) so that the recurrence warps of a new
+// CTA start after a short fill of the filter pipeline; the others have p.ts samples.
+#ifndef AIDAX_TC3_TS0
+#define AIDAX_TC3_TS0 8 // measured on B200 (LSTM-16, 378880 streams): 0: 1721, 2: 1715, 4: 1707, 8: 1695 us per period
+#endif
+struct SubBlocks {
+    int n, ts, ts0, count;
+    __device__ __forceinline__ SubBlocks(int n_samples, int ts_)
+        : n(n_samples), ts(ts_), ts0((AIDAX_TC3_TS0 > 0 && AIDAX_TC3_TS0 < ts_ && n_samples > AIDAX_TC3_TS0) ? AIDAX_TC3_TS0 : ts_)
+    {
+        count = n <= ts0 ? 1 : 1 + (n - ts0 + ts - 1) / ts;
+    }
+    __device__ __forceinline__ int start(int k) const { return k == 0 ? 0 : ts0 + (k - 1) * ts; }
+    __device__ __forceinline__ int len(int k) const { return k == 0 ? min(ts0, n) : min(ts, n - start(k)); }
+};
+
 enum : int { CF_PREWARM = 1, CF_NET = 2 }; // CTA-wide flag word written by the filter warps before the first barrier
 
 // the five EQ bands as five passes over the tile (filter warps run with a small register budget; pass_eq's software
 // pipeline keeps 5 x 7 doubles live).  Same values: stage k's input is the float stage k-1 left in the tile.
+#ifndef AIDAX_TC3_WIDEN_INT
+#define AIDAX_TC3_WIDEN_INT 0 // 1: the filter warps widen float -> double with integer instructions (BiquadReg::widen): 7 of the 114 XU lane-ops per stream-sample
+#endif
 #ifndef AIDAX_TC3_PREFETCH
 #define AIDAX_TC3_PREFETCH 0 // 1: a filter pass asks for the NEXT pass's coefficients and state (L1) before it starts its own loop
 #endif
@@ -98,7 +143,7 @@ __device__ __forceinline__ void pass_eq_serial(float* xcol, int ts, const Stream
 #pragma unroll 1
     for (int k = k0; k <= k1; ++k) {
         prefetch_bq(sa, k < k1 ? k + 1 : next_which, slot);
-        pass_biquad<XP>(xcol, ts, sa, k, slot);
+        pass_biquad<XP, AIDAX_TC3_WIDEN_INT>(xcol, ts, sa, k, slot);
     }
 }
 
@@ -110,7 +155,9 @@ __global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW>::NTH, RES) chain_kerne
     using Cell = Tc2Cell<CELL, H, SPLIT, true, false, MATH>;
     using Base = TcCell<CELL, H, MATH>;
     constexpr int XP = Sh::XP, NTH = Sh::NTH, CS = Sh::CS, UH = Sh::UH, NRW = Sh::NRW, NBUF = Sh::NBUF;
-    constexpr uint32_t BAR_ALL = 15; // named barrier of the whole CTA (the roles meet from different code paths)
+    // The roles meet from different code paths, so the CTA-wide rendezvous are mbarriers (every thread arrives, then waits for
+    // phase 0), not bar.sync: each is passed once per launch.  Hand-overs through `full` / `done` are arrivals of EVERY lane of
+    // the producing warp (each thread releases its own shared-memory writes; compute-sanitizer's racecheck follows that).
     extern __shared__ __align__(128) float smem_tc3[];
     float* smem = smem_tc3;
 
@@ -165,9 +212,11 @@ __global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW>::NTH, RES) chain_kerne
         tc::mbar_init(&bars[1], 1);
 #pragma unroll 1
         for (int i = 0; i < 8 * NBUF; ++i) {
-            tc::mbar_init(&bars[2 + i], 1);                 // full: one arrival, the filter warp's lane 0
-            tc::mbar_init(&bars[2 + 8 * NBUF + i], SPLIT);  // done: lane 0 of every recurrence warp of the warp-tile
+            tc::mbar_init(&bars[2 + i], 32);                     // full: the lanes of the warp-tile's filter warp
+            tc::mbar_init(&bars[2 + 8 * NBUF + i], 32 * SPLIT);  // done: the lanes of every recurrence warp of the warp-tile
         }
+#pragma unroll 1
+        for (int i = 0; i < 3; ++i) tc::mbar_init(&bars[2 + 16 * NBUF + i], NTH);
         *cta_flags = 0;
         tc::mbar_init_fence();
     }
@@ -180,7 +229,13 @@ __global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW>::NTH, RES) chain_kerne
 
     const int tile_floats = p.ts * XP * (1 + n_ptiles + Sh::YB);
     const uint32_t full0 = tc::smem_u32(&bars[2]), done0 = tc::smem_u32(&bars[2 + 8 * NBUF]);
-    const int nsb = (p.n_samples + p.ts - 1) / p.ts;
+    const uint32_t meet0 = tc::smem_u32(&bars[2 + 16 * NBUF]);
+    auto rendezvous = [&](int which) {
+        tc::mbar_arrive(meet0 + 8 * which);
+        tc::mbar_wait(meet0 + 8 * which, 0u);
+    };
+    const SubBlocks sb(p.n_samples, p.ts);
+    const int nsb = sb.count;
 
     if (warp >= NRW) {
         // =====================================================================================================
@@ -209,9 +264,9 @@ __global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW>::NTH, RES) chain_kerne
             if (lane == 0 && cf) atomicOr(cta_flags, cf);
         }
         __threadfence_block();
-        tc::bar_sync(BAR_ALL, NTH);                       // (A) slot flags, CTA flags and the commands' effects are visible
+        rendezvous(0);                                    // (A) slot flags, CTA flags and the commands' effects are visible
         const int cf = *reinterpret_cast<volatile int*>(cta_flags);
-        if (cf & CF_PREWARM) tc::bar_sync(BAR_ALL, NTH);  // (A2) the recurrence warps have read the parked param values
+        if (cf & CF_PREWARM) rendezvous(1);               // (A2) the recurrence warps have read the parked param values
         const bool any_net = (cf & CF_NET) != 0;
 
 #pragma unroll 1
@@ -230,8 +285,8 @@ __global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW>::NTH, RES) chain_kerne
 
                 // ---- sub-block k - NBUF: stages after the network (run(), rt-neural-generic.cpp:645-655), write back
                 if (k >= NBUF) {
-                    const int j = k - NBUF, t0 = j * p.ts, ts = min(p.ts, p.n_samples - t0);
-                    if (any_net) tc::mbar_wait(done0 + 8 * (wt * NBUF + b), (uint32_t)(j / NBUF) & 1u);
+                    const int j = k - NBUF, t0 = sb.start(j), ts = sb.len(j);
+                    if (any_net) tc::mbar_wait_relaxed(done0 + 8 * (wt * NBUF + b), (uint32_t)(j / NBUF) & 1u);
                     if (live) {
                         if constexpr (SPLIT > 1) {
                             // Dense partial sums of the parts + skip + output gain (applyModel, :170-182)
@@ -251,12 +306,12 @@ __global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW>::NTH, RES) chain_kerne
                         const bool dc_on = (flags & F_DC) != 0;
                         if (flags & F_EQ_POST) {
                             prefetch_bq(sa, (flags & F_EQ_BANDPASS) ? BQ_MID : BQ_DEPTH, cslot);
-                            if (dc_on) pass_biquad<XP>(xcol, ts, sa, BQ_DC, cslot);
+                            if (dc_on) pass_biquad<XP, AIDAX_TC3_WIDEN_INT>(xcol, ts, sa, BQ_DC, cslot);
                             pass_eq_serial<XP>(xcol, ts, sa, cslot, (flags & F_EQ_BANDPASS) != 0, BQ_INLPF);
-                            pass_dc_master<XP>(xcol, ts, sa, cslot, false, true);
+                            pass_dc_master<XP, AIDAX_TC3_WIDEN_INT>(xcol, ts, sa, cslot, false, true);
                         } else {
                             prefetch_bq(sa, BQ_INLPF, cslot);
-                            pass_dc_master<XP>(xcol, ts, sa, cslot, dc_on, true);
+                            pass_dc_master<XP, AIDAX_TC3_WIDEN_INT>(xcol, ts, sa, cslot, dc_on, true);
                         }
                     }
                     __syncwarp();
@@ -265,14 +320,14 @@ __global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW>::NTH, RES) chain_kerne
                 }
                 // ---- sub-block k: stage in, stages before the network (:622-644), hand over
                 if (k < nsb) {
-                    const int t0 = k * p.ts, ts = min(p.ts, p.n_samples - t0);
+                    const int t0 = sb.start(k), ts = sb.len(k);
                     load_tile<32, XP>(xb, p, ws, t0, ts, lane);
                     __syncwarp();
                     float* p1b = n_ptiles >= 1 ? xb + p.ts * XP : nullptr;
                     float* p2b = n_ptiles >= 2 ? xb + 2 * p.ts * XP : nullptr;
                     if (live) {
                         if (flags & F_EQ_PRE) prefetch_bq(sa, (flags & F_EQ_BANDPASS) ? BQ_MID : BQ_DEPTH, cslot);
-                        pass_lpf_pregain<XP>(xcol, ts, sa, cslot, (flags & F_LPF) != 0);
+                        pass_lpf_pregain<XP, AIDAX_TC3_WIDEN_INT>(xcol, ts, sa, cslot, (flags & F_LPF) != 0);
                         if (flags & F_EQ_PRE) pass_eq_serial<XP>(xcol, ts, sa, cslot, (flags & F_EQ_BANDPASS) != 0, BQ_DC);
                         if (flags & F_NET) {
                             const uint32_t dfl = sa.dflags[cslot];
@@ -289,7 +344,7 @@ __global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW>::NTH, RES) chain_kerne
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(full0 + 8 * (wt * NBUF + b));
+                    tc::mbar_arrive(full0 + 8 * (wt * NBUF + b));
                 }
             }
         }
@@ -330,7 +385,7 @@ __global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW>::NTH, RES) chain_kerne
             for (int c = H / 4; c < S::KP / 4; ++c) Cell::store_chunk(tt[0], c, 0.f, 0.f, 0.f, 0.f);
         }
 
-        tc::bar_sync(BAR_ALL, NTH);                       // (A)
+        rendezvous(0);                                    // (A)
         const int cf = *reinterpret_cast<volatile int*>(cta_flags);
         const int sf = sflags[g * 128 + row];
         const int rslot = max(wslots[g * 128 + row], 0);
@@ -345,7 +400,7 @@ __global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW>::NTH, RES) chain_kerne
             ln[0].p1c = sa.p_mem[rslot];
             ln[0].p2c = sa.p_mem[(size_t)sa.cap + rslot];
             ln[0].commit = false;
-            tc::bar_sync(BAR_ALL, NTH);                   // (A2) from here on the filter warps may advance the param smoothers
+            rendezvous(1);                                // (A2) from here on the filter warps may advance the param smoothers
             float cst[1][UH];
             Cell::load_state(tt[0], cst[0], sa, rslot, false, hs * UH);
             Cell::run(tt, cst, ln, dw, kPrewarmSteps, md.in_gain, md.out_gain, md.in_skip != 0, hs, issuer, db_hi, db_lo);
@@ -358,7 +413,7 @@ __global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW>::NTH, RES) chain_kerne
             Cell::load_state(tt[0], cst[0], sa, rslot, (sf & SF_VALID) != 0, hs * UH);
 #pragma unroll 1
             for (int k = 0; k < nsb; ++k) {
-                const int b = k % NBUF, t0 = k * p.ts, ts = min(p.ts, p.n_samples - t0);
+                const int b = k % NBUF, ts = sb.len(k);
                 float* xb = audio + (size_t)(b * 8 + wt) * tile_floats;
                 tc::mbar_wait(full0 + 8 * (wt * NBUF + b), (uint32_t)(k / NBUF) & 1u);
                 typename Cell::Lane ln[1];
@@ -370,14 +425,14 @@ __global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW>::NTH, RES) chain_kerne
                 ln[0].commit = rnet;
                 Cell::run(tt, cst, ln, dw, ts, md.in_gain, md.out_gain, md.in_skip != 0, hs, issuer, db_hi, db_lo);
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(done0 + 8 * (wt * NBUF + b));
+                tc::mbar_arrive(done0 + 8 * (wt * NBUF + b));
             }
             Cell::store_state(tt[0], cst[0], sa, rslot, hs * UH, rnet);
         }
     }
 
     tc::tc_fence_before();
-    tc::bar_sync(BAR_ALL, NTH);
+    rendezvous(2);
     if (warp == 0) tc::tmem_dealloc(tmem_base, Sh::tmem_cols());
 }
 

@@ -42,7 +42,18 @@ def timing(hs):
                 run(n, hidden, tile_mode=3, iters=10)
 
 
+def sanitizer_run():
+    """A short generation-3 scenario for compute-sanitizer (memcheck / racecheck / synccheck): model binding inside the run,
+    ragged periods, conditioned inputs, a partly empty last CTA."""
+    for hidden, cell, insz in ((16, 0, 1), (40, 1, 3)):
+        y, launches = render(2 * 256 + 70, hidden, cell, insz, {"AIDAX_TC_GEN": "3"}, 3, 0, [128, 100, 28, 128])
+        print("san H=%d cell=%d: %d launches, finite %s, peak %.4f" % (hidden, cell, launches, bool(np.isfinite(y).all()), float(np.abs(y).max())), flush=True)
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "san":
+        sanitizer_run()
+        sys.exit(0)
     if sys.argv[1] == "check":
         if len(sys.argv) > 3:
             sys.exit(check((int(sys.argv[2]), int(sys.argv[3]))))
