@@ -249,22 +249,6 @@ def e2e_arm(args, wl, paths, n_inst, first_global, n_global, rank, world, local_
     from aidadsp_lv2_b200 import signals, engine as engmod
     period_s = T / FS
     host_threads = args.host_threads or max(1, _host_cores() // world)
-    host = ax.BatchHost(ax.plugin_path(), n_instances=n_inst, max_block=T, n_threads=host_threads, device=local_rank)
-    for port in range(4, 25):
-        if port != 23:
-            host.set_control(port, float(wl.controls[port - 4]))
-    if len(wl.models) == 1:
-        host.load_model(paths[0])
-    else:
-        for s in range(n_inst):
-            host.load_model(paths[wl.model_of_stream(first_global + s, n_global)], instance=s)
-    blk = signals.sweep_noise_block(min(n_inst, 256), T)
-    host.input[:, :T] = np.tile(blk, ((n_inst + blk.shape[0] - 1) // blk.shape[0], 1))[:n_inst]
-    for i in range(5):
-        host.run(T)   # model load + 2048-sample pre-warm + fade-in happen here
-    assert host.batched
-    assert host.get_control("MODELINSIZE") == wl.models[wl.model_of_stream(first_global, n_global)].input_size
-
     # the copy ceiling with every rank copying at once: what the box's PCIe / host memory gives this GPU under load
     pcie = None
     try:
@@ -282,6 +266,32 @@ def e2e_arm(args, wl, paths, n_inst, first_global, n_global, rank, world, local_
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
             pcie = None
+
+    # The hand-over granularity follows the copy rate: a chunk should cost ~0.17 ms of copy time in each direction (16384
+    # instances at the 49 GB/s of a lone GPU; on the 8-GPU box of this pool every GPU gets ~12 GB/s when all ranks copy at once,
+    # and a 16384-instance chunk would be a quarter of the period).  Set before the plugin's engine is created; an explicit
+    # AIDAX_BATCH_CHUNK wins.
+    chunk = CHUNK
+    if pcie and "AIDAX_BATCH_CHUNK" not in os.environ:
+        chunk = max(2048, min(CHUNK, int(round(pcie[2] * 340 / 2048)) * 2048))
+        os.environ["AIDAX_BATCH_CHUNK"] = str(chunk)
+    elif "AIDAX_BATCH_CHUNK" in os.environ:
+        chunk = int(os.environ["AIDAX_BATCH_CHUNK"])
+    host = ax.BatchHost(ax.plugin_path(), n_instances=n_inst, max_block=T, n_threads=host_threads, device=local_rank)
+    for port in range(4, 25):
+        if port != 23:
+            host.set_control(port, float(wl.controls[port - 4]))
+    if len(wl.models) == 1:
+        host.load_model(paths[0])
+    else:
+        for s in range(n_inst):
+            host.load_model(paths[wl.model_of_stream(first_global + s, n_global)], instance=s)
+    blk = signals.sweep_noise_block(min(n_inst, 256), T)
+    host.input[:, :T] = np.tile(blk, ((n_inst + blk.shape[0] - 1) // blk.shape[0], 1))[:n_inst]
+    for i in range(5):
+        host.run(T)   # model load + 2048-sample pre-warm + fade-in happen here
+    assert host.batched
+    assert host.get_control("MODELINSIZE") == wl.models[wl.model_of_stream(first_global, n_global)].input_size
 
     points = {}
 
@@ -357,7 +367,7 @@ def e2e_arm(args, wl, paths, n_inst, first_global, n_global, rank, world, local_
            "path": "aidax-batch-host -> #batch begin() -> run_block() over the instances (control-row scan; run() only for instances with events or changed "
                    "controls) -> each completed chunk of instances is shipped at once (aidax_render_host_submit: pinned H2D -> kernels -> D2H on separate "
                    "CUDA streams) -> end() waits" if bulk else "aidax-batch-host -> run() x N -> chunks shipped as they complete -> end() waits",
-           "bulk_run_block": bool(bulk), "host_threads": host_threads, "host_cpus": cpus, "timer": "wall clock per period (the call returns after D2H + stream synchronise); mean over steps, max over ranks",
+           "bulk_run_block": bool(bulk), "chunk_instances": chunk, "host_threads": host_threads, "host_cpus": cpus, "timer": "wall clock per period (the call returns after D2H + stream synchronise); mean over steps, max over ranks",
            "gpu_launches": main["launches"]}
     e2e.update(extra)
     if pcie:

@@ -39,10 +39,14 @@ def test_bundled_golden_vectors(native_libs, bundled_models, tile_mode):
         eng.activate(s)             # gain smoothers jump to 1.0
     x = np.stack([m.input_batch for m in ms])
     y = eng.render_host(x)
-    # 1e-5 is the reference's own self-test threshold (TEST_MODEL_THR).  The tensor-core shape with fast-math gates
-    # (MUFU ex2 + batched rcp) measures 1.0e-6 .. 9.9e-6 on these vectors -- on the line for the hottest capture -- so it is
-    # held to 2e-5 here (the reference's own SSE2-vs-AVX2 build difference) and to 1e-5 in precise mode below.
-    tol = 2e-5 if tile_mode == 3 else 1e-5
+    # 1e-5 is the reference's own self-test threshold (TEST_MODEL_THR).  Every shape keeps it with the fast gates (MUFU ex2 +
+    # batched rcp): measured on B200 7.4e-7 .. 7.4e-6 in the tensor-core shape, .. 7.0e-6 in the FP32 shapes, and <= 2.2e-6 with
+    # precise gate math (profiles/r02r_golden_margins.txt).  The kernels are deterministic, so the margin is stable.
+    tol = 1e-5
+    # per-capture margins in the test output (pytest -rP; tools/golden_err.py prints the same table for every shape and
+    # math mode: profiles/r02r_golden_margins.txt)
+    print("golden vectors, tile_mode %d, max abs error per capture (reference threshold 1e-5, held to %.0e here): %s" %
+          (tile_mode, tol, "  ".join("%s %.2e" % (bundled_models[i].split("/")[-1], np.abs(y[i] - m.output_batch).max()) for i, m in enumerate(ms))))
     for i, m in enumerate(ms):
         err = np.abs(y[i] - m.output_batch).max()
         assert err <= tol, (bundled_models[i], err)
