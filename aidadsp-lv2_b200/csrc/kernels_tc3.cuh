@@ -9,11 +9,14 @@
 //   * recurrence warps (R): 2 tiles of 128 streams per CTA, SPLIT warps per TMEM lane quadrant.  They do nothing but
 //     Tc2Cell::run -- wait for the MMA, gate epilogue, write h(t) and x(t+1) into the A operand in TENSOR MEMORY, hand
 //     the tile back to the tensor core -- for the whole period, sub-block after sub-block.
-//   * filter warps (F): ONE warpgroup per CTA.  Lane l of F warp q owns streams (tile 0, row 32 q + l) and (tile 1, same
-//     row): it stages their audio, runs the stages in front of the network for sub-block k+1 and the stages behind it
-//     for sub-block k-1 while the R warps work on sub-block k.  Sub-blocks travel through a two-deep ring of shared-memory
-//     tiles guarded by mbarriers (`full`: F -> R, `done`: R -> F), one pair per warp-tile of 32 streams, so that no R warp
-//     ever waits for a filter stage (F has ~10x slack) and no block-wide barrier sits in the period.
+//   * filter warps (F): NFW warps per CTA in whole warpgroups -- 8 in the shipped shapes, one per warp-tile of 32 streams
+//     (lane l owns stream 32 wt + l; with NFW = 4 a lane owns two streams and runs them one after the other).  An F warp
+//     stages its streams' audio, runs the stages in front of the network for sub-block k+1 and the stages behind it for
+//     sub-block k-1 while the R warps work on sub-block k.  Sub-blocks travel through a two-deep ring of shared-memory
+//     tiles guarded by mbarriers (`full`: F -> R, `done`: R -> F), one pair per warp-tile and ring slot, so that no
+//     block-wide barrier sits in the period and the R warps wait for a filter stage only while the pipeline fills.
+//     (Measured on B200: with 4 F warps -- one per scheduler -- the R warps spent 13 % of their time waiting on `full`,
+//     a lone F warp cannot hide its own dependency latency; 8 F warps cover for each other.)
 //   * `setmaxnreg` moves registers from the F warpgroup (FREG) to the R warpgroups (RREG): the launch carries
 //     65536 / (threads x CTAs per SM) registers per thread and the roles re-split them.
 //
@@ -63,30 +66,31 @@ template <int N>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 } // namespace tc
 
-template <int H, int SPLIT, int NFW = 4>
+template <int H, int SPLIT, int NFW = 8, int NTILES = 2>
 struct Tc3Shape {
     using S = TcShape<H>;
     static constexpr int N = S::N, KP = S::KP, XP = S::XP;
     static constexpr int UH = H / SPLIT;
     static constexpr int GROUP = 128 * SPLIT;  // recurrence threads of one tile (meet at its named barrier)
-    static constexpr int NR = 2 * GROUP;       // recurrence threads
+    static constexpr int NR = NTILES * GROUP;  // recurrence threads
     static constexpr int NRW = NR / 32;
     static constexpr int NTH = NR + 32 * NFW;  // + the filter warps: one or two warpgroups
-    static constexpr int FS = 8 / NFW;         // warp-tiles (streams per lane) of a filter warp
-    static_assert(NFW == 4 || NFW == 8, "filter warps come in whole warpgroups");
+    static constexpr int NWT = 4 * NTILES;     // warp-tiles of 32 streams
+    static constexpr int FS = NWT / NFW;       // warp-tiles (streams per lane) of a filter warp
+    static_assert(NFW % 4 == 0 && NWT % NFW == 0, "filter warps come in whole warpgroups and share the warp-tiles evenly");
     static constexpr int NW = NTH / 32;
-    static constexpr int CS = 256;             // streams per CTA: two tiles of 128
+    static constexpr int CS = 128 * NTILES;    // streams per CTA: NTILES tiles of 128
     static constexpr int NBUF = 2;             // ring depth of the audio sub-block tiles
     static constexpr int YB = SPLIT > 1 ? SPLIT : 0;
     static constexpr int TILE_COLS = N + 2 * KP; // TMEM columns of one tile: accumulator | A hi | A lo
-    static constexpr int NBARS = 2 + 2 * 8 * NBUF + 3; // MMA completion per tile, full / done per (warp-tile, ring slot), 3 CTA-wide rendezvous
+    static constexpr int NBARS = NTILES + 2 * NWT * NBUF + 3; // MMA completion per tile, full / done per (warp-tile, ring slot), 3 CTA-wide rendezvous
     static_assert(H % SPLIT == 0 && UH % 4 == 0, "the units of a thread must be whole 16-column accumulator chunks");
-    static_assert(2 * TILE_COLS <= 512, "two tiles must fit tensor memory");
+    static_assert(NTILES * TILE_COLS <= 512, "the tiles must fit tensor memory");
 
     __host__ __device__ static constexpr int tmem_cols()
     {
         int c = 32;
-        while (c < 2 * TILE_COLS) c *= 2;
+        while (c < NTILES * TILE_COLS) c *= 2;
         return c;
     }
     __host__ __device__ static constexpr int fixed_floats()
@@ -94,7 +98,7 @@ struct Tc3Shape {
         return 2 * S::B_FLOATS + (H + 4) + 2 * NBARS + 8 /* tmem base, CTA flag word, pad */ + 2 * CS /* slot table, per-stream flags */;
     }
     // the ring of audio tiles (8 warp-tiles of 32 streams per slot), expressed per launch warp as the engine sizes it
-    __host__ __device__ static constexpr int warp_floats(int ts, int n_param_tiles) { return (NBUF * 8 * ts * XP * (1 + n_param_tiles + YB) + NW - 1) / NW; }
+    __host__ __device__ static constexpr int warp_floats(int ts, int n_param_tiles) { return (NBUF * NWT * ts * XP * (1 + n_param_tiles + YB) + NW - 1) / NW; }
 };
 
 // Sub-block schedule of a period: the FIRST sub-block is short (AIDAX_TC3_TS0 samples) so that the recurrence warps of a new
@@ -147,14 +151,14 @@ __device__ __forceinline__ void pass_eq_serial(float* xcol, int ts, const Stream
     }
 }
 
-template <int CELL, int H, int SPLIT, int NFW, int RREG, int FREG, int RES, int MATH>
-__global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW>::NTH, RES) chain_kernel_tc3(const __grid_constant__ RenderParams p)
+template <int CELL, int H, int SPLIT, int NFW, int RREG, int FREG, int RES, int MATH, int NTILES = 2>
+__global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW, NTILES>::NTH, RES) chain_kernel_tc3(const __grid_constant__ RenderParams p)
 {
-    using Sh = Tc3Shape<H, SPLIT, NFW>;
+    using Sh = Tc3Shape<H, SPLIT, NFW, NTILES>;
     using S = TcShape<H>;
     using Cell = Tc2Cell<CELL, H, SPLIT, true, false, MATH>;
     using Base = TcCell<CELL, H, MATH>;
-    constexpr int XP = Sh::XP, NTH = Sh::NTH, CS = Sh::CS, UH = Sh::UH, NRW = Sh::NRW, NBUF = Sh::NBUF;
+    constexpr int XP = Sh::XP, NTH = Sh::NTH, CS = Sh::CS, UH = Sh::UH, NRW = Sh::NRW, NBUF = Sh::NBUF, NWT = Sh::NWT;
     // The roles meet from different code paths, so the CTA-wide rendezvous are mbarriers (every thread arrives, then waits for
     // phase 0), not bar.sync: each is passed once per launch.  Hand-overs through `full` / `done` are arrivals of EVERY lane of
     // the producing warp (each thread releases its own shared-memory writes; compute-sanitizer's racecheck follows that).
@@ -208,15 +212,15 @@ __global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW>::NTH, RES) chain_kerne
         }
     }
     if (tid == 0) {
-        tc::mbar_init(&bars[0], 1);
-        tc::mbar_init(&bars[1], 1);
 #pragma unroll 1
-        for (int i = 0; i < 8 * NBUF; ++i) {
-            tc::mbar_init(&bars[2 + i], 32);                     // full: the lanes of the warp-tile's filter warp
-            tc::mbar_init(&bars[2 + 8 * NBUF + i], 32 * SPLIT);  // done: the lanes of every recurrence warp of the warp-tile
+        for (int i = 0; i < NTILES; ++i) tc::mbar_init(&bars[i], 1);
+#pragma unroll 1
+        for (int i = 0; i < NWT * NBUF; ++i) {
+            tc::mbar_init(&bars[NTILES + i], 32);                       // full: the lanes of the warp-tile's filter warp
+            tc::mbar_init(&bars[NTILES + NWT * NBUF + i], 32 * SPLIT);  // done: the lanes of every recurrence warp of the warp-tile
         }
 #pragma unroll 1
-        for (int i = 0; i < 3; ++i) tc::mbar_init(&bars[2 + 16 * NBUF + i], NTH);
+        for (int i = 0; i < 3; ++i) tc::mbar_init(&bars[NTILES + 2 * NWT * NBUF + i], NTH);
         *cta_flags = 0;
         tc::mbar_init_fence();
     }
@@ -228,8 +232,8 @@ __global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW>::NTH, RES) chain_kerne
     const uint32_t tmem_base = *tmem_slot;
 
     const int tile_floats = p.ts * XP * (1 + n_ptiles + Sh::YB);
-    const uint32_t full0 = tc::smem_u32(&bars[2]), done0 = tc::smem_u32(&bars[2 + 8 * NBUF]);
-    const uint32_t meet0 = tc::smem_u32(&bars[2 + 16 * NBUF]);
+    const uint32_t full0 = tc::smem_u32(&bars[NTILES]), done0 = tc::smem_u32(&bars[NTILES + NWT * NBUF]);
+    const uint32_t meet0 = tc::smem_u32(&bars[NTILES + 2 * NWT * NBUF]);
     auto rendezvous = [&](int which) {
         tc::mbar_arrive(meet0 + 8 * which);
         tc::mbar_wait(meet0 + 8 * which, 0u);
@@ -277,7 +281,7 @@ __global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW>::NTH, RES) chain_kerne
                 const int* ws = wslots + wt * 32;
                 const int cslot = ws[lane];
                 const int b = k % NBUF;
-                float* xb = audio + (size_t)(b * 8 + wt) * tile_floats;
+                float* xb = audio + (size_t)(b * NWT + wt) * tile_floats;
                 float* xcol = xb + lane;
                 uint32_t flags = 0;
                 if (cslot >= 0) flags = sa.flags[cslot];
@@ -405,7 +409,7 @@ __global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW>::NTH, RES) chain_kerne
             Cell::load_state(tt[0], cst[0], sa, rslot, false, hs * UH);
             Cell::run(tt, cst, ln, dw, kPrewarmSteps, md.in_gain, md.out_gain, md.in_skip != 0, hs, issuer, db_hi, db_lo);
             Cell::store_state(tt[0], cst[0], sa, rslot, hs * UH, (sf & SF_PREWARM) != 0);
-            tc::bar_sync(3 + g, Sh::GROUP);               // every part's state is in global memory before anyone reloads it
+            tc::bar_sync(8 + g, Sh::GROUP);               // every part's state is in global memory before anyone reloads it
         }
 
         float cst[1][UH]; // recurrent state of this thread's units, in registers across the whole period
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW>::NTH, RES) chain_kerne
 #pragma unroll 1
             for (int k = 0; k < nsb; ++k) {
                 const int b = k % NBUF, ts = sb.len(k);
-                float* xb = audio + (size_t)(b * 8 + wt) * tile_floats;
+                float* xb = audio + (size_t)(b * NWT + wt) * tile_floats;
                 tc::mbar_wait(full0 + 8 * (wt * NBUF + b), (uint32_t)(k / NBUF) & 1u);
                 typename Cell::Lane ln[1];
                 ln[0].xcol = xb + lane;

@@ -52,15 +52,17 @@ static int wsf_tc2(int ts, int np) { return Tc2Shape<H, SPLIT, ATM, PP>::warp_fl
 #ifndef AIDAX_TC3_NFW
 #define AIDAX_TC3_NFW 8 // filter warps per CTA (4: two streams per lane, 8: one)
 #endif
-template <int H, int SPLIT>
-static int wsf_tc3(int ts, int np) { return Tc3Shape<H, SPLIT, AIDAX_TC3_NFW>::warp_floats(ts, np); }
-#define TC3_SHAPE(Hh, SPL) Tc3Shape<Hh, SPL, AIDAX_TC3_NFW>
-#define VT3(CELL, Hh, SPL, RR, FR, RES)                                                                  \
-    { CELL, Hh, SPL, 5, TC3_SHAPE(Hh, SPL)::NW, 256 / TC3_SHAPE(Hh, SPL)::NW,                            \
-      { (const void*)&chain_kernel_tc3<CELL, Hh, SPL, AIDAX_TC3_NFW, RR, FR, RES, 0>,                    \
-        (const void*)&chain_kernel_tc3<CELL, Hh, SPL, AIDAX_TC3_NFW, RR, FR, RES, 1> },                  \
-      &wsf_tc3<Hh, SPL>, 3, (TC3_SHAPE(Hh, SPL)::fixed_floats() + 3) & ~3, RES, 256 }
-#define BOTH_TC3(Hh, SPL, RR, FR, RES) VT3(0, Hh, SPL, RR, FR, RES), VT3(1, Hh, SPL, RR, FR, RES)
+template <int H, int SPLIT, int NFWv, int NT>
+static int wsf_tc3(int ts, int np) { return Tc3Shape<H, SPLIT, NFWv, NT>::warp_floats(ts, np); }
+#define TC3_SHAPE(Hh, SPL, NFWv, NT) Tc3Shape<Hh, SPL, NFWv, NT>
+#define VT3(CELL, Hh, SPL, NFWv, RR, FR, RES, NT)                                                        \
+    { CELL, Hh, SPL, 5, TC3_SHAPE(Hh, SPL, NFWv, NT)::NW, TC3_SHAPE(Hh, SPL, NFWv, NT)::CS / TC3_SHAPE(Hh, SPL, NFWv, NT)::NW, \
+      { (const void*)&chain_kernel_tc3<CELL, Hh, SPL, NFWv, RR, FR, RES, 0, NT>,                         \
+        (const void*)&chain_kernel_tc3<CELL, Hh, SPL, NFWv, RR, FR, RES, 1, NT> },                       \
+      &wsf_tc3<Hh, SPL, NFWv, NT>, 3, (TC3_SHAPE(Hh, SPL, NFWv, NT)::fixed_floats() + 3) & ~3, RES, TC3_SHAPE(Hh, SPL, NFWv, NT)::CS }
+#define BOTH_TC3(Hh, SPL, RR, FR, RES) VT3(0, Hh, SPL, AIDAX_TC3_NFW, RR, FR, RES, 2), VT3(1, Hh, SPL, AIDAX_TC3_NFW, RR, FR, RES, 2)
+// three tiles per CTA, one CTA per SM, one filter warp per warp-tile (12): 768 threads launch with 80 registers
+#define BOTH_TC3_3T(Hh, RR, FR) VT3(0, Hh, 1, 12, RR, FR, 1, 3), VT3(1, Hh, 1, 12, RR, FR, 1, 3)
 
 #ifndef AIDAX_TC_NT32
 #define AIDAX_TC_NT32 3
@@ -133,8 +135,15 @@ static int wsf_w(int ts, int np) { return WShape::warp_floats(ts, np); }
 #ifndef AIDAX_TC3_LIST_20
 #define AIDAX_TC3_LIST_20 BOTH_TC3(20, 1, AIDAX_TC3_RREG, AIDAX_TC3_FREG, 2),
 #endif
+#ifndef AIDAX_TC3_H24_THREE_TILES
+#define AIDAX_TC3_H24_THREE_TILES 1 // H = 24: three tiles per CTA (tensor memory holds 3 x 160 columns), one CTA per SM, 12 + 12 warps at 128 / 32 registers: 1446 vs 1716 us (generation 1) per 227328-stream period, bit-identical
+#endif
 #ifndef AIDAX_TC3_LIST_24
-#define AIDAX_TC3_LIST_24 // measured slower than generation 1 at GPU-filling counts (2040 vs 1961 us per 262144-stream period)
+#if AIDAX_TC3_H24_THREE_TILES
+#define AIDAX_TC3_LIST_24 BOTH_TC3_3T(24, 128, 32),
+#else
+#define AIDAX_TC3_LIST_24 // (two tiles with SPLIT 2 measured slower than generation 1: 2040 vs 1961 us per 262144-stream period)
+#endif
 #endif
 #ifndef AIDAX_TC3_LIST_32
 #define AIDAX_TC3_LIST_32 BOTH_TC3(32, 2, AIDAX_TC3_RREG2, AIDAX_TC3_FREG2, 1),

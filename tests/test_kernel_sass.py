@@ -11,8 +11,8 @@ import pytest
 
 import aidadsp_lv2_b200 as ax
 
-# chain_kernel_tc3<CELL=LSTM, H=16, SPLIT=1, NFW=8, RREG=96, FREG=32, RES=2, MATH=fast>
-KERNEL = "_ZN5aidax16chain_kernel_tc3ILi0ELi16ELi1ELi8ELi96ELi32ELi2ELi0EEEvNS_12RenderParamsE"
+# chain_kernel_tc3<CELL=LSTM, H=16, SPLIT=1, NFW=8, RREG=96, FREG=32, RES=2, MATH=fast, NTILES=2>
+KERNEL = "_ZN5aidax16chain_kernel_tc3ILi0ELi16ELi1ELi8ELi96ELi32ELi2ELi0ELi2EEEvNS_12RenderParamsE"
 
 
 @pytest.fixture(scope="module")

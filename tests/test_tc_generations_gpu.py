@@ -3,7 +3,7 @@ against the first-generation tensor-core kernel (kernels_tc.cuh, AIDAX_TC_GEN=1)
 
 Same arithmetic, other schedule: recurrence warps and filter warps are decoupled through a shared-memory ring, the A
 operand lives in tensor memory, the five EQ bands run as five passes.  Where a stream's hidden units stay in one thread
-(H <= 20) the output must be BIT-IDENTICAL; where they are split over two warps (H = 32, 40) only the order of the Dense
+(H <= 24) the output must be BIT-IDENTICAL; where they are split over two warps (H = 32, 40) only the order of the Dense
 partial sums differs (<= 2e-6).  The scenario covers both cells, conditioned inputs, EQ before and after the network,
 bypassed and disabled streams, a model bound in the middle of the run (device-side pre-warm) and ragged period lengths;
 the oracle comparison of the same shapes is tests/test_engine_gpu.py (tile_mode 3)."""
@@ -52,14 +52,14 @@ def _render(n, hidden, cell, insz, gen, ts_max=None):
     return np.concatenate(outs, axis=1)
 
 
-@pytest.mark.parametrize("cell,hidden,insz", [(0, 16, 1), (1, 16, 3), (0, 8, 1), (1, 12, 2), (0, 20, 2), (0, 32, 1), (1, 40, 3), (0, 40, 2)])
+@pytest.mark.parametrize("cell,hidden,insz", [(0, 16, 1), (1, 16, 3), (0, 8, 1), (1, 12, 2), (0, 20, 2), (0, 24, 1), (1, 24, 3), (0, 32, 1), (1, 40, 3), (0, 40, 2)])
 def test_warp_specialised_kernel_matches_generation_1(native_libs, cell, hidden, insz):
-    n = 2 * 256 + 130  # ragged: the last CTA has a partly empty second tile
+    n = 2 * 384 + 130  # ragged: the last CTA has a partly empty tile (CTAs hold 256 streams, 384 for H = 24)
     ref = _render(n, hidden, cell, insz, 1)
     y = _render(n, hidden, cell, insz, 3)
     assert np.isfinite(y).all()
     d = float(np.abs(y - ref).max())
-    if hidden <= 20:
+    if hidden <= 24:
         assert d == 0.0, d
     else:
         assert d <= 2e-6, d

@@ -8,7 +8,7 @@ sys.path.insert(0, "."); sys.path.insert(0, "tools")
 import numpy as np
 from tc2_check import render
 
-HS = [int(v) for v in os.environ.get("TC3_HS", "8 12 16 20").split()]
+HS = [int(v) for v in os.environ.get("TC3_HS", "8 12 16 20 24 32 40").split()]
 
 
 def check(only=None):
@@ -23,7 +23,7 @@ def check(only=None):
             ref1, _ = render(n, hidden, cell, insz, {"AIDAX_TC_GEN": "1"}, 3, 0, periods)
             y, launches = render(n, hidden, cell, insz, {"AIDAX_TC_GEN": "3"}, 3, 0, periods)
             d1 = float(np.abs(y - ref1).max())
-            split1 = hidden <= 20
+            split1 = hidden <= 24
             ok = np.isfinite(y).all() and (d1 == 0.0 if split1 else d1 < 2e-6)
             bad += 0 if ok else 1
             print("H=%2d cell=%d in=%d gen3 vs gen1: %.3g  %s" % (hidden, cell, insz, d1, "ok" if ok else "MISMATCH"), flush=True)
