@@ -109,6 +109,7 @@ struct aidax_engine {
     std::mutex mu;
     int tile_mode = 0, math_mode = 0;
     int tc_min_streams = 4096; // auto mode: families at least this large run on the tensor-core variant
+    int tc3_tiles = 0;         // AIDAX_TC3_TILES: 0 auto, 1 one-tile CTAs, 2 multi-tile CTAs (see choose_variant)
     int ts_max = 0;            // AIDAX_TS_MAX: cap of the sub-block length (measurement knob; results do not depend on it)
     int tc_gen = 3, tc2_split = -1, tc2_atmem = -1; // which tensor-core kernel generation / shape (see choose_variant)
     int sm_count = 148;
@@ -360,7 +361,26 @@ static const KernelVariant* choose_variant(const aidax_engine* e, const Family& 
         // shapes (measurement builds), default = the first one listed
         // generation 3 = the warp-specialised shapes of kernels_tc3.cuh (S bit 2), generation 2 = the two-tile shapes
         if (e->tc_gen >= 2 && !fam.tc2.empty()) {
-            for (int gen = e->tc_gen; gen >= 2; --gen) {
+            if (e->tc_gen == 3) {
+                // Warp-specialised shapes come with one tile of 128 streams per CTA and with two (three) tiles.  A family that
+                // cannot give every SM a multi-tile CTA pair runs one-tile CTAs: twice as many CTAs, half the recurrence warps
+                // per scheduler, so a period's 128 dependent time steps finish sooner (hand-over chunks of the host-fed path,
+                // the families of a mixed-model period).  AIDAX_TC3_TILES = 1 / 2 pins the one-tile / multi-tile shape.
+                const KernelVariant *one = nullptr, *multi = nullptr;
+                for (const KernelVariant* kv : fam.tc2)
+                    if (kv->S & 4) {
+                        if (kv->cs == 128) { if (!one) one = kv; }
+                        else if (!multi) multi = kv;
+                    }
+                // measured on B200 (profiles/r02w_tc3_one_tile.txt): LSTM-16 152 vs 214 us per period up to 16384 streams, level at
+                // 32768, multi-tile ahead beyond; LSTM-40 340 vs 418 us up to 16384, behind at 32768; LSTM-24 (three-tile CTAs,
+                // one per SM) 211 vs 354 us up to 16384 and still 300 vs 355 us at 32768
+                const int one_tile_max = e->sm_count * ((multi && multi->cs > 256) ? 256 : 128);
+                const bool want_one = e->tc3_tiles == 1 || (e->tc3_tiles == 0 && n_streams <= one_tile_max);
+                if (one && (want_one || !multi)) return one;
+                if (multi) return multi;
+            }
+            for (int gen = std::min(e->tc_gen, 2); gen >= 2; --gen) {
                 for (const KernelVariant* kv : fam.tc2)
                     if (((kv->S & 4) != 0) == (gen == 3) && (e->tc2_split < 0 || kv->L == e->tc2_split) &&
                         (e->tc2_atmem < 0 || (kv->S & 3) == (e->tc2_atmem & 3)))
@@ -598,6 +618,7 @@ int aidax_engine_create(int device, int max_streams, int max_block, aidax_engine
     if (const char* v = std::getenv("AIDAX_TC_MIN_STREAMS")) e->tc_min_streams = std::atoi(v);
     if (const char* v = std::getenv("AIDAX_TC_GEN")) e->tc_gen = std::min(3, std::max(1, std::atoi(v)));
     if (const char* v = std::getenv("AIDAX_TS_MAX")) e->ts_max = std::atoi(v);
+    if (const char* v = std::getenv("AIDAX_TC3_TILES")) e->tc3_tiles = std::atoi(v);
     if (const char* v = std::getenv("AIDAX_TC2_SPLIT")) e->tc2_split = std::atoi(v);
     if (const char* v = std::getenv("AIDAX_TC2_ATMEM")) e->tc2_atmem = std::atoi(v);
     if (const char* v = std::getenv("AIDAX_TILE_MODE")) e->tile_mode = std::max(0, std::min(std::atoi(v), 3)); // initial kernel-shape choice (aidax_engine_configure overrides)

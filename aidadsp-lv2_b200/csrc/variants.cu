@@ -61,6 +61,8 @@ static int wsf_tc3(int ts, int np) { return Tc3Shape<H, SPLIT, NFWv, NT>::warp_f
         (const void*)&chain_kernel_tc3<CELL, Hh, SPL, NFWv, RR, FR, RES, 1, NT> },                       \
       &wsf_tc3<Hh, SPL, NFWv, NT>, 3, (TC3_SHAPE(Hh, SPL, NFWv, NT)::fixed_floats() + 3) & ~3, RES, TC3_SHAPE(Hh, SPL, NFWv, NT)::CS }
 #define BOTH_TC3(Hh, SPL, RR, FR, RES) VT3(0, Hh, SPL, AIDAX_TC3_NFW, RR, FR, RES, 2), VT3(1, Hh, SPL, AIDAX_TC3_NFW, RR, FR, RES, 2)
+// one tile per CTA (the shape for launches that underfill the GPU): 4 SPLIT recurrence warps + 4 filter warps
+#define BOTH_TC3_1T(Hh, SPL, RR, FR, RES) VT3(0, Hh, SPL, 4, RR, FR, RES, 1), VT3(1, Hh, SPL, 4, RR, FR, RES, 1)
 // three tiles per CTA, one CTA per SM, one filter warp per warp-tile (12): 768 threads launch with 80 registers
 #define BOTH_TC3_3T(Hh, RR, FR) VT3(0, Hh, 1, 12, RR, FR, 1, 3), VT3(1, Hh, 1, 12, RR, FR, 1, 3)
 
@@ -124,32 +126,32 @@ static int wsf_w(int ts, int np) { return WShape::warp_floats(ts, np); }
 #define AIDAX_TC3_FREG2 (AIDAX_TC3_NFW == 8 ? 32 : 64)
 #endif
 #ifndef AIDAX_TC3_LIST_8
-#define AIDAX_TC3_LIST_8 BOTH_TC3(8, 1, AIDAX_TC3_RREG, AIDAX_TC3_FREG, 2),
+#define AIDAX_TC3_LIST_8 BOTH_TC3(8, 1, AIDAX_TC3_RREG, AIDAX_TC3_FREG, 2), BOTH_TC3_1T(8, 1, 96, 32, 4),
 #endif
 #ifndef AIDAX_TC3_LIST_12
-#define AIDAX_TC3_LIST_12 BOTH_TC3(12, 1, AIDAX_TC3_RREG, AIDAX_TC3_FREG, 2),
+#define AIDAX_TC3_LIST_12 BOTH_TC3(12, 1, AIDAX_TC3_RREG, AIDAX_TC3_FREG, 2), BOTH_TC3_1T(12, 1, 96, 32, 4),
 #endif
 #ifndef AIDAX_TC3_LIST_16
-#define AIDAX_TC3_LIST_16 BOTH_TC3(16, 1, AIDAX_TC3_RREG, AIDAX_TC3_FREG, 2),
+#define AIDAX_TC3_LIST_16 BOTH_TC3(16, 1, AIDAX_TC3_RREG, AIDAX_TC3_FREG, 2), BOTH_TC3_1T(16, 1, 96, 32, 4),
 #endif
 #ifndef AIDAX_TC3_LIST_20
-#define AIDAX_TC3_LIST_20 BOTH_TC3(20, 1, AIDAX_TC3_RREG, AIDAX_TC3_FREG, 2),
+#define AIDAX_TC3_LIST_20 BOTH_TC3(20, 1, AIDAX_TC3_RREG, AIDAX_TC3_FREG, 2), BOTH_TC3_1T(20, 1, 96, 32, 4),
 #endif
 #ifndef AIDAX_TC3_H24_THREE_TILES
 #define AIDAX_TC3_H24_THREE_TILES 1 // H = 24: three tiles per CTA (tensor memory holds 3 x 160 columns), one CTA per SM, 12 + 12 warps at 128 / 32 registers: 1446 vs 1716 us (generation 1) per 227328-stream period, bit-identical
 #endif
 #ifndef AIDAX_TC3_LIST_24
 #if AIDAX_TC3_H24_THREE_TILES
-#define AIDAX_TC3_LIST_24 BOTH_TC3_3T(24, 128, 32),
+#define AIDAX_TC3_LIST_24 BOTH_TC3_3T(24, 128, 32), BOTH_TC3_1T(24, 1, 128, 32, 2),
 #else
 #define AIDAX_TC3_LIST_24 // (two tiles with SPLIT 2 measured slower than generation 1: 2040 vs 1961 us per 262144-stream period)
 #endif
 #endif
 #ifndef AIDAX_TC3_LIST_32
-#define AIDAX_TC3_LIST_32 BOTH_TC3(32, 2, AIDAX_TC3_RREG2, AIDAX_TC3_FREG2, 1),
+#define AIDAX_TC3_LIST_32 BOTH_TC3(32, 2, AIDAX_TC3_RREG2, AIDAX_TC3_FREG2, 1), BOTH_TC3_1T(32, 2, 104, 32, 2),
 #endif
 #ifndef AIDAX_TC3_LIST_40
-#define AIDAX_TC3_LIST_40 BOTH_TC3(40, 2, AIDAX_TC3_RREG2, AIDAX_TC3_FREG2, 1),
+#define AIDAX_TC3_LIST_40 BOTH_TC3(40, 2, AIDAX_TC3_RREG2, AIDAX_TC3_FREG2, 1), BOTH_TC3_1T(40, 2, 104, 32, 2),
 #endif
 
 #define CAT_(a, b) a##b

@@ -20,11 +20,13 @@ pytestmark = pytest.mark.gpu
 PERIODS = [128, 128, 128, 100, 28, 128]
 
 
-def _render(n, hidden, cell, insz, gen, ts_max=None):
-    saved = {k: os.environ.get(k) for k in ("AIDAX_TC_GEN", "AIDAX_TS_MAX")}
+def _render(n, hidden, cell, insz, gen, ts_max=None, tiles=None):
+    saved = {k: os.environ.get(k) for k in ("AIDAX_TC_GEN", "AIDAX_TS_MAX", "AIDAX_TC3_TILES")}
     os.environ["AIDAX_TC_GEN"] = str(gen)
     if ts_max:
         os.environ["AIDAX_TS_MAX"] = str(ts_max)
+    if tiles:
+        os.environ["AIDAX_TC3_TILES"] = str(tiles)
     try:
         eng = ax.Engine(max_streams=n, max_block=128)
     finally:
@@ -52,11 +54,12 @@ def _render(n, hidden, cell, insz, gen, ts_max=None):
     return np.concatenate(outs, axis=1)
 
 
+@pytest.mark.parametrize("tiles", [1, 2])  # one tile of 128 streams per CTA (what a small family gets) / two or three tiles
 @pytest.mark.parametrize("cell,hidden,insz", [(0, 16, 1), (1, 16, 3), (0, 8, 1), (1, 12, 2), (0, 20, 2), (0, 24, 1), (1, 24, 3), (0, 32, 1), (1, 40, 3), (0, 40, 2)])
-def test_warp_specialised_kernel_matches_generation_1(native_libs, cell, hidden, insz):
-    n = 2 * 384 + 130  # ragged: the last CTA has a partly empty tile (CTAs hold 256 streams, 384 for H = 24)
+def test_warp_specialised_kernel_matches_generation_1(native_libs, cell, hidden, insz, tiles):
+    n = 2 * 384 + 130  # ragged: the last CTA has a partly empty tile (CTAs hold 128, 256 or -- H = 24 -- 384 streams)
     ref = _render(n, hidden, cell, insz, 1)
-    y = _render(n, hidden, cell, insz, 3)
+    y = _render(n, hidden, cell, insz, 3, tiles=tiles)
     assert np.isfinite(y).all()
     d = float(np.abs(y - ref).max())
     if hidden <= 24:
@@ -69,6 +72,6 @@ def test_warp_specialised_kernel_matches_generation_1(native_libs, cell, hidden,
 def test_warp_specialised_kernel_does_not_depend_on_the_sub_block_length(native_libs, ts_max):
     """The ring hands sub-blocks of `ts` samples from the filter warps to the recurrence warps; the output must not depend on ts."""
     n = 256 + 40
-    a = _render(n, 16, 0, 1, 3)
-    b = _render(n, 16, 0, 1, 3, ts_max=ts_max)
+    a = _render(n, 16, 0, 1, 3, tiles=2)
+    b = _render(n, 16, 0, 1, 3, ts_max=ts_max, tiles=1 + ts_max % 3 % 2)
     assert np.array_equal(a, b)
