@@ -1,7 +1,7 @@
 #!/bin/bash
-# Round 2, GPU call R: the round's evidence on HEAD (warp-specialised kernel as shipped): GPU suite, smoke, both bench arms,
+# Round 2, GPU call X: the round's evidence on HEAD (warp-specialised kernel as shipped): GPU suite, smoke, both bench arms,
 # C3/C4/C5, golden-vector margins, ncu launch list + full captures.
-TAG=${1:-r02r}
+TAG=${1:-r02x}
 OUT=$PWD/gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.max.sm,pcie.link.gen.current,pcie.link.width.current --format=csv > $OUT/${TAG}_gpu_box.txt 2>&1
@@ -20,7 +20,7 @@ for w in c3 c4 c5; do
 done
 python - <<'PY'
 import json, glob
-for name in sorted(glob.glob("gpurun_out/r02r_bench*.json")):
+for name in sorted(glob.glob("gpurun_out/r02x_bench*.json")):
     try:
         d = json.load(open(name)); e = d["e2e"]
         print(name, "value %.4e" % d["value"], "dev ms", d["ms_per_step"], "| e2e %.4e" % e["value"], "n", e.get("streams_per_gpu"), "us", e.get("us_per_buffer"), "p95", e.get("us_p95"), "meets", e.get("meets_deadline"), d.get("roofline", {}).get("bound"), d.get("roofline", {}).get("frac"))
