@@ -108,7 +108,7 @@ struct aidax_engine {
     cudaStream_t stream = nullptr;
     std::mutex mu;
     int tile_mode = 0, math_mode = 0;
-    int tc_min_streams = 4096; // auto mode: families at least this large run on the tensor-core variant
+    int tc_min_streams = 0;    // AIDAX_TC_MIN_STREAMS: > 0 overrides the family size from which auto mode takes the tensor-core shape (tc_threshold)
     int tc3_tiles = 0;         // AIDAX_TC3_TILES: 0 auto, 1 one-tile CTAs, 2 multi-tile CTAs (see choose_variant)
     int ts_max = 0;            // AIDAX_TS_MAX: cap of the sub-block length (measurement knob; results do not depend on it)
     int tc_gen = 3, tc2_split = -1, tc2_atmem = -1; // which tensor-core kernel generation / shape (see choose_variant)
@@ -348,14 +348,40 @@ static int upload_dirty(aidax_engine* e, int first, int n, cudaStream_t st)
     return AIDAX_OK;
 }
 
-static const KernelVariant* choose_variant(const aidax_engine* e, const Family& fam, int n_streams)
+// Family size from which auto mode takes the tensor-core shape.  Measured on B200 with the one-tile warp-specialised kernel
+// against the FP32 shapes, one family alone on the GPU (profiles/r02aa_small_families.txt, us per 128-sample period at
+// 512 / 1024 / 2048 / 4096 streams): H 20: 200 201 206 208 (FP32) vs 188 189 189 190 -> 512;  H 24: 154 154 154 236 vs 210 ->
+// 3072;  H 32: 121 158 283 472 vs 261 -> 2048;  H 40: 340 340 341 541 vs 340 -> 2048;  H <= 16: the warp-per-stream shape wins up
+// to 40 streams per SM (76 / 129 us at 2048 / 4096 vs 152), checked first in choose_variant.
+// `range_streams` = all streams of the range being planned: when a mixed-model period is large enough to fill the GPU
+// anyway (C4 sharded over 2 / 4 GPUs: 14 families of 2340 / 1170 streams), the families compete for throughput, not for
+// latency, and the tensor-core shape renders a stream with a fraction of the FP32 shapes' issue slots: every family of at
+// least 512 streams takes it then.
+static int tc_threshold(const aidax_engine* e, const Family& fam, int range_streams)
+{
+    if (e->tc_min_streams > 0) return e->tc_min_streams;
+    const bool loaded = range_streams >= e->sm_count * 64;
+    if (loaded) return 512;
+    switch (fam.H) {
+    case 20: return 512;
+    case 24: return 3072;
+    case 32: case 40: return 2048;
+    default: return 4096;
+    }
+}
+
+static const KernelVariant* choose_variant(const aidax_engine* e, const Family& fam, int n_streams, int range_streams)
 {
     const auto& v = fam.variants;
+    const int tc_min = tc_threshold(e, fam, range_streams);
+    const bool loaded = e->tc_min_streams <= 0 && range_streams >= e->sm_count * 64 && range_streams > n_streams;
     // auto: small batches take the warp-per-stream shape while it is the fastest (measured on B200, LSTM-16: 76 vs 113 us
     // per period at 2048 streams, 129 vs 207 us at 4096 -- register-tiled and tensor-core shape alike --, 234 vs 207 us
     // at 8192) ...
-    if (e->tile_mode == 0 && !v.empty() && v.front()->kind == 2 && n_streams <= e->sm_count * 40) return v.front();
-    if ((fam.tc || !fam.tc2.empty()) && (e->tile_mode == 3 || (e->tile_mode == 0 && n_streams >= e->tc_min_streams))) {
+    // (in a loaded mixed-model period only below the tensor-core threshold: one warp per stream is the most expensive way to
+    // render a stream once the GPU is full)
+    if (e->tile_mode == 0 && !v.empty() && v.front()->kind == 2 && n_streams <= e->sm_count * 40 && !(loaded && n_streams >= tc_min)) return v.front();
+    if ((fam.tc || !fam.tc2.empty()) && (e->tile_mode == 3 || (e->tile_mode == 0 && n_streams >= tc_min))) {
         // a two-tile shape of kernels_tc2.cuh where one is compiled for this hidden size (variants.cu lists only shapes that
         // beat the first generation), unless AIDAX_TC_GEN=1; AIDAX_TC2_SPLIT / AIDAX_TC2_ATMEM pick among several compiled
         // shapes (measurement builds), default = the first one listed
@@ -424,6 +450,8 @@ static int build_plan(aidax_engine* e, int first, int n, RangePlan** out)
     rp.launches.clear();
     e->h_tables.clear();
     const int last = std::min(first + n, e->n_open_hi);
+    int range_streams = 0; // streams of the range that run a network (the launch planner's view of how full the GPU will be)
+    for (int s = first; s < last; ++s) range_streams += (e->streams[s].open && e->streams[s].model >= 0) ? 1 : 0;
     for (const Family& fam : e->families) {
         // gather (model, slot) pairs of this family, grouped by model
         std::map<int, std::vector<int>> by_model;
@@ -440,7 +468,7 @@ static int build_plan(aidax_engine* e, int first, int n, RangePlan** out)
         }
         if (!total) continue;
         LaunchPlan lp;
-        lp.kv = choose_variant(e, fam, total);
+        lp.kv = choose_variant(e, fam, total, range_streams);
         const int CS = lp.kv->cs ? lp.kv->cs : lp.kv->ws * lp.kv->NW;
         std::vector<int> blk_model, blk_slots, all_slots;
         for (auto& kv : by_model) {

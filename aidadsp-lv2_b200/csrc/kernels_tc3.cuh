@@ -6,7 +6,7 @@
 // alternating between the two phases (4 warps per scheduler, 128 registers each) the pipe that bounds the kernel is busy
 // 61 % of the time.  Here the two roles get their own warps and their own register budgets:
 //
-//   * recurrence warps (R): 2 tiles of 128 streams per CTA, SPLIT warps per TMEM lane quadrant.  They do nothing but
+//   * recurrence warps (R): NTILES tiles of 128 streams per CTA (1, 2 or 3), SPLIT warps per TMEM lane quadrant.  They do nothing but
 //     Tc2Cell::run -- wait for the MMA, gate epilogue, write h(t) and x(t+1) into the A operand in TENSOR MEMORY, hand
 //     the tile back to the tensor core -- for the whole period, sub-block after sub-block.
 //   * filter warps (F): NFW warps per CTA in whole warpgroups -- 8 in the shipped shapes, one per warp-tile of 32 streams
@@ -74,7 +74,7 @@ struct Tc3Shape {
     static constexpr int GROUP = 128 * SPLIT;  // recurrence threads of one tile (meet at its named barrier)
     static constexpr int NR = NTILES * GROUP;  // recurrence threads
     static constexpr int NRW = NR / 32;
-    static constexpr int NTH = NR + 32 * NFW;  // + the filter warps: one or two warpgroups
+    static constexpr int NTH = NR + 32 * NFW;  // + the filter warps: whole warpgroups
     static constexpr int NWT = 4 * NTILES;     // warp-tiles of 32 streams
     static constexpr int FS = NWT / NFW;       // warp-tiles (streams per lane) of a filter warp
     static_assert(NFW % 4 == 0 && NWT % NFW == 0, "filter warps come in whole warpgroups and share the warp-tiles evenly");
@@ -97,7 +97,7 @@ struct Tc3Shape {
     {
         return 2 * S::B_FLOATS + (H + 4) + 2 * NBARS + 8 /* tmem base, CTA flag word, pad */ + 2 * CS /* slot table, per-stream flags */;
     }
-    // the ring of audio tiles (8 warp-tiles of 32 streams per slot), expressed per launch warp as the engine sizes it
+    // the ring of audio tiles (NWT warp-tiles of 32 streams per slot), expressed per launch warp as the engine sizes it
     __host__ __device__ static constexpr int warp_floats(int ts, int n_param_tiles) { return (NBUF * NWT * ts * XP * (1 + n_param_tiles + YB) + NW - 1) / NW; }
 };
 
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(Tc3Shape<H, SPLIT, NFW, NTILES>::NTH, RES) cha
     float* Bh = smem;
     float* Bl = Bh + S::B_FLOATS;
     float* dw = Bl + S::B_FLOATS;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(dw + H + 4); // [0..1] MMA completion; then full[8][NBUF], done[8][NBUF]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dw + H + 4); // [NTILES] MMA completion; then full[NWT][NBUF], done[NWT][NBUF], 3 rendezvous
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Sh::NBARS);
     int* cta_flags = reinterpret_cast<int*>(tmem_slot + 1);
     int* wslots = reinterpret_cast<int*>(tmem_slot + 8);
