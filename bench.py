@@ -335,6 +335,25 @@ def e2e_arm(args, wl, paths, n_inst, first_global, n_global, rank, world, local_
             if nxt == n or (mean_s <= period_s and nxt < n):
                 break
             n = nxt
+        # refine between the largest count that met the deadline and the smallest that did not (the proportional steps above
+        # stop at the 4096 grain): bisect, at most three more points
+        for _ in range(3):
+            passing = [k for k in points if points[k]["meets_deadline"]]
+            failing = [k for k in points if not points[k]["meets_deadline"]]
+            if not passing or not failing:
+                break
+            lo, hi = max(passing), min(k for k in failing if k > max(passing)) if any(k > max(passing) for k in failing) else None
+            if hi is None or hi - lo <= GRAIN:
+                break
+            mid = (lo + hi) // 2 // GRAIN * GRAIN
+            if world > 1:
+                t = torch.tensor([mid], device=dev, dtype=torch.int64)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                mid = int(t.item())
+            if mid in points or mid <= lo:
+                break
+            if point(mid, 10) <= period_s:
+                best = mid
         n_rt = best if best is not None else min(points, key=lambda k: points[k]["us_per_buffer"])
         point(n_rt, args.e2e_steps)   # the reported measurement
         # real time means (nearly) every period: the reported count must also keep the 95th percentile inside the deadline

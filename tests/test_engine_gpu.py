@@ -41,10 +41,10 @@ def test_bundled_golden_vectors(native_libs, bundled_models, tile_mode):
     y = eng.render_host(x)
     # 1e-5 is the reference's own self-test threshold (TEST_MODEL_THR).  Every shape keeps it with the fast gates (MUFU ex2 +
     # batched rcp): measured on B200 7.4e-7 .. 7.4e-6 in the tensor-core shape, .. 7.0e-6 in the FP32 shapes, and <= 2.2e-6 with
-    # precise gate math (profiles/r02x_golden_margins.txt).  The kernels are deterministic, so the margin is stable.
+    # precise gate math (profiles/r02final_golden_margins.txt).  The kernels are deterministic, so the margin is stable.
     tol = 1e-5
     # per-capture margins in the test output (pytest -rP; tools/golden_err.py prints the same table for every shape and
-    # math mode: profiles/r02x_golden_margins.txt)
+    # math mode: profiles/r02final_golden_margins.txt)
     print("golden vectors, tile_mode %d, max abs error per capture (reference threshold 1e-5, held to %.0e here): %s" %
           (tile_mode, tol, "  ".join("%s %.2e" % (bundled_models[i].split("/")[-1], np.abs(y[i] - m.output_batch).max()) for i, m in enumerate(ms))))
     for i, m in enumerate(ms):

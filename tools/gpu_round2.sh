@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round 2, GPU call X: the round's evidence on HEAD (warp-specialised kernel as shipped): GPU suite, smoke, both bench arms,
+# Round 2: the round's evidence on HEAD (gpurun -- 'bash tools/gpu_round2.sh TAG') (warp-specialised kernel as shipped): GPU suite, smoke, both bench arms,
 # C3/C4/C5, golden-vector margins, ncu launch list + full captures.
 TAG=${1:-r02x}
 OUT=$PWD/gpurun_out
@@ -18,9 +18,9 @@ timeout 900 python bench.py --steps 20 --warmup 5 > $OUT/${TAG}_bench.json 2> $O
 for w in c3 c4 c5; do
   timeout 600 python bench.py --workload $w --steps 20 --warmup 5 --no-cpu-baseline > $OUT/${TAG}_bench_$w.json 2> /dev/null; echo "$w exit $?"
 done
-python - <<'PY'
-import json, glob
-for name in sorted(glob.glob("gpurun_out/r02x_bench*.json")):
+TAG=$TAG python - <<'PY'
+import json, glob, os
+for name in sorted(glob.glob("gpurun_out/%s_bench*.json" % os.environ["TAG"])):
     try:
         d = json.load(open(name)); e = d["e2e"]
         print(name, "value %.4e" % d["value"], "dev ms", d["ms_per_step"], "| e2e %.4e" % e["value"], "n", e.get("streams_per_gpu"), "us", e.get("us_per_buffer"), "p95", e.get("us_p95"), "meets", e.get("meets_deadline"), d.get("roofline", {}).get("bound"), d.get("roofline", {}).get("frac"))
