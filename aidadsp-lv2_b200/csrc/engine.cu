@@ -1585,6 +1585,32 @@ int aidax_measure_pcie(int device, size_t bytes, double gbs_out[3])
 
 uint64_t aidax_engine_launch_count(aidax_engine* e) { return e ? e->launches : 0; }
 
+int aidax_engine_describe_plan(aidax_engine* e, int first_stream, int n_streams, char* out, int cap)
+{
+    if (!e || !out || cap < 1) return fail(AIDAX_ERR_ARG, "bad describe_plan arguments");
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (first_stream < 0 || n_streams < 0 || first_stream + n_streams > e->cap) return fail(AIDAX_ERR_ARG, "bad stream range");
+    CUDA_TRY(cudaSetDevice(e->device));
+    RangePlan* rp = nullptr;
+    const int rc = build_plan(e, first_stream, n_streams, &rp);
+    if (rc) return rc;
+    static const char* const kKind[] = {"fp32", "tc1", "warp", "tc2"};
+    std::string text;
+    for (const LaunchPlan& lp : rp->launches) {
+        const KernelVariant* kv = lp.kv;
+        int streams = 0;
+        for (const auto& r : lp.runs) streams += r.second - r.first;
+        const int cs = kv->cs ? kv->cs : kv->ws * kv->NW;
+        char line[160];
+        snprintf(line, sizeof(line), "%s H=%d shape=%s streams=%d ctas=%d streams_per_cta=%d threads=%d\n",
+                 kv->cell == 0 ? "lstm" : kv->cell == 1 ? "gru" : "none", kv->cell == 2 ? 0 : kv->H,
+                 (kv->kind == 3 && (kv->S & 4)) ? "tc3" : kKind[kv->kind & 3], streams, lp.n_blocks, cs, kv->NW * 32);
+        text += line;
+    }
+    snprintf(out, (size_t)cap, "%s", text.c_str());
+    return AIDAX_OK;
+}
+
 int aidax_engine_pci_bus_id(aidax_engine* e, char* out, int cap)
 {
     if (!e || !out || cap < 13) return fail(AIDAX_ERR_ARG, "bad pci_bus_id arguments");

@@ -67,6 +67,7 @@ def load_library():
     lib.aidax_model_release.argtypes = [vp, C.c_int]
     lib.aidax_model_selftest.argtypes = [vp, C.c_int, fp, ip, ip]
     lib.aidax_engine_pci_bus_id.argtypes = [vp, C.c_char_p, C.c_int]
+    lib.aidax_engine_describe_plan.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, C.c_int]
     lib.aidax_stream_open.argtypes = [vp, C.c_double, ip]
     lib.aidax_stream_close.argtypes = [vp, C.c_int]
     lib.aidax_stream_activate.argtypes = [vp, C.c_int]
@@ -174,6 +175,20 @@ class Engine:
         buf = C.create_string_buffer(64)
         self._chk(self.lib.aidax_engine_pci_bus_id(self.h, buf, 64))
         return buf.value.decode()
+
+    def describe_plan(self, first=0, n=None):
+        """The planner's launches for a stream range: list of dicts (cell, H, shape, streams, ctas, streams_per_cta, threads)."""
+        buf = C.create_string_buffer(1 << 14)
+        self._chk(self.lib.aidax_engine_describe_plan(self.h, first, self.max_streams if n is None else n, buf, len(buf)))
+        out = []
+        for line in buf.value.decode().splitlines():
+            f = line.split()
+            d = {"cell": f[0]}
+            for kv in f[1:]:
+                k, v = kv.split("=")
+                d[k] = v if k == "shape" else int(v)
+            out.append(d)
+        return out
 
     def selftest_model(self, mid):
         """The reference's load-time testModel on the GPU: (max abs error, samples above 1e-5, samples compared)."""

@@ -273,6 +273,13 @@ int aidax_measure_pcie(int device, size_t bytes, double gbs_out[3]);
  * arenas on the GPU's NUMA node (/sys/bus/pci/devices/<id>/local_cpulist). */
 int aidax_engine_pci_bus_id(aidax_engine* e, char* out, int cap);
 
+/* Diagnostic: the launches the planner would issue for the streams [first_stream, first_stream + n_streams) in the
+ * engine's current configuration, one text line per kernel family, largest footprint first:
+ *   "<lstm|gru|none> H=<hidden> shape=<warp|fp32|tc1|tc2|tc3> streams=<n> ctas=<n> streams_per_cta=<n> threads=<n>"
+ * (warp = warp-per-stream latency shape, fp32 = register-tiled, tc1..tc3 = tensor-core generations; tc3 with 128
+ * streams per CTA is the one-tile shape).  Truncated to `cap` bytes. */
+int aidax_engine_describe_plan(aidax_engine* e, int first_stream, int n_streams, char* out, int cap);
+
 /* Number of kernel launches issued by the engine since creation (for bench accounting). */
 uint64_t aidax_engine_launch_count(aidax_engine* e);
 
