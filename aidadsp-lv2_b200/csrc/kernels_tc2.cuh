@@ -32,6 +32,9 @@ namespace tc {
 // Wait for a tile's MMA completion.  AIDAX_MMA_POLL_NS = 0: mbarrier.try_wait with a suspend-time hint (the warp parks, but
 // NANOSLEEP.SYNCS wakes on every mbarrier event of the CTA and re-issues the check: ~15 wake-ups of 5 instructions per
 // wait in the warp-specialised kernel); > 0: test_wait + a plain nanosleep of that length.
+#ifndef AIDAX_TC2_EARLY_X
+#define AIDAX_TC2_EARLY_X 0
+#endif
 #ifndef AIDAX_MMA_POLL_NS
 #define AIDAX_MMA_POLL_NS 0
 #endif
@@ -297,6 +300,21 @@ struct Tc2Cell {
 #endif
                 tc::tc_fence_after();
 
+#if AIDAX_TC2_EARLY_X
+                // The next step's input columns do not depend on this step's epilogue, and the MMAs that read x(t) are
+                // complete: x(t+1) goes into the A row first, so that its shared-memory load, split and tcgen05.st are off
+                // the tail of the step (only the h chunks and the store wait remain in front of the hand-over).
+                const float xg_now = xg[g];
+                if (t + 1 < n && hs == 0) {
+                    xg[g] = ln[g].xcol ? ln[g].xcol[(t + 1) * XP] * in_gain : 0.f;
+                    const float v1 = ln[g].p1col ? ln[g].p1col[(t + 1) * XP] : ln[g].p1c;
+                    const float v2 = ln[g].p2col ? ln[g].p2col[(t + 1) * XP] : ln[g].p2c;
+                    store_chunk(tt[g], H / 4, xg[g], v1, v2, 1.0f);
+                }
+#else
+                const float xg_now = xg[g];
+#endif
+
                 // epilogue of this thread's units: pairs of 16-column chunks (8 hidden units) as one straight-line block
                 float2 y2 = make_float2(db, 0.f);
 #pragma unroll
@@ -327,13 +345,13 @@ struct Tc2Cell {
                 // dense + skip + output gain (applyModel, rt-neural-generic.cpp:170-182); with the units split over several
                 // threads the halves' partial sums are combined after the sub-block (combine_halves)
                 if constexpr (SPLIT == 1) {
-                    if (ln[g].xcol && ln[g].commit) ln[g].xcol[t * XP] = (in_skip ? xg[g] + y : y) * out_gain;
+                    if (ln[g].xcol && ln[g].commit) ln[g].xcol[t * XP] = (in_skip ? xg_now + y : y) * out_gain;
                 } else {
                     if (ln[g].ycol) ln[g].ycol[t * XP] = y;
                 }
                 // input columns of the next step, then hand the tile back to the tensor core
                 if (t + 1 < n) {
-                    if (hs == 0) {
+                    if (hs == 0 && !AIDAX_TC2_EARLY_X) {
                         xg[g] = ln[g].xcol ? ln[g].xcol[(t + 1) * XP] * in_gain : 0.f;
                         const float v1 = ln[g].p1col ? ln[g].p1col[(t + 1) * XP] : ln[g].p1c;
                         const float v2 = ln[g].p2col ? ln[g].p2col[(t + 1) * XP] : ln[g].p2c;
