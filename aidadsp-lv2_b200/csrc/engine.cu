@@ -382,10 +382,9 @@ static const KernelVariant* choose_variant(const aidax_engine* e, const Family& 
     // render a stream once the GPU is full)
     if (e->tile_mode == 0 && !v.empty() && v.front()->kind == 2 && n_streams <= e->sm_count * 40 && !(loaded && n_streams >= tc_min)) return v.front();
     if ((fam.tc || !fam.tc2.empty()) && (e->tile_mode == 3 || (e->tile_mode == 0 && n_streams >= tc_min))) {
-        // a two-tile shape of kernels_tc2.cuh where one is compiled for this hidden size (variants.cu lists only shapes that
-        // beat the first generation), unless AIDAX_TC_GEN=1; AIDAX_TC2_SPLIT / AIDAX_TC2_ATMEM pick among several compiled
-        // shapes (measurement builds), default = the first one listed
-        // generation 3 = the warp-specialised shapes of kernels_tc3.cuh (S bit 2), generation 2 = the two-tile shapes
+        // AIDAX_TC_GEN: 3 (default) = the warp-specialised shapes of kernels_tc3.cuh (S bit 2), 2 = the two-tile shapes of
+        // kernels_tc2.cuh where one is compiled for this hidden size (AIDAX_TC2_SPLIT / AIDAX_TC2_ATMEM pick among several in
+        // measurement builds), 1 = kernels_tc.cuh
         if (e->tc_gen >= 2 && !fam.tc2.empty()) {
             if (e->tc_gen == 3) {
                 // Warp-specialised shapes come with one tile of 128 streams per CTA and with two (three) tiles.  A family that
